@@ -1,0 +1,932 @@
+// libdpt_b200.so - host side of the C ABI declared in include/dpt_b200.h: weight registry, workspace arena, launch
+// plans (recorded once per (shape, buffers), replayed afterwards) and the stage builders that mirror the reference's
+// five sub-models (muggled_dpt/dpt_model.py:61-83).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "dpt_b200.h"
+#include "attn_tc.cuh"
+#include "gemm_tc.cuh"
+#include "kernels_misc.cuh"
+
+using namespace dpt;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small utilities
+
+thread_local std::string g_err;  // errors without a handle (dpt_create, dpt_op_*)
+
+struct Weight {
+  const void* ptr = nullptr;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int ndim = 0;
+  int dtype = 0;
+};
+
+using LaunchFn = std::function<cudaError_t(cudaStream_t)>;
+
+struct Plan {
+  std::vector<LaunchFn> launches;
+  // cache key
+  const void* img = nullptr;
+  const void* out = nullptr;
+  const void* ws = nullptr;
+  int B = 0, H = 0, W = 0;
+  bool valid = false;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  bool overflow = false;
+  void* alloc(size_t n) {
+    off = (off + 1023) & ~size_t(1023);
+    void* p = dry ? nullptr : base + off;
+    off += n;
+    if (off > peak) peak = off;
+    if (!dry && off > cap) overflow = true;
+    return p;
+  }
+  size_t mark() const { return off; }
+  void reset(size_t m) { off = m; }
+};
+
+}  // namespace
+
+struct dpt_model_s {
+  dpt_config cfg;
+  std::unordered_map<std::string, Weight> weights;
+  std::unordered_map<std::string, std::vector<float>> host_copies;  // "*_host" weights (tiny, read at plan time)
+  std::string err;
+  Plan fwd_plan;
+  int last_launches = 0;
+  int num_sms = 148;
+  int device = 0;
+};
+
+namespace {
+
+struct Ctx {
+  dpt_model_s* m;
+  Arena ar;
+  std::vector<LaunchFn>* launches;  // null in dry mode
+  bool dry;
+  std::string err;
+  bool ok = true;
+  int is_bf16;
+  int num_sms;
+  bool fail(const std::string& s) {
+    if (ok) err = s;
+    ok = false;
+    return false;
+  }
+};
+
+PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// 16-bit tensor map with 128B swizzle. dims/box innermost first; strides in bytes for dims 1..rank-1.
+bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+               const uint32_t* box, int is_bf16, std::string& err) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  if (!enc) {
+    err = "cuTensorMapEncodeTiled not available (no CUDA driver?)";
+    return false;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t d[5], s[5];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
+  CUresult r = enc(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                   const_cast<void*>(ptr), d, s, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u] ptr=%p",
+             (int)r, rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+             (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0), bx[0],
+             rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0, ptr);
+    err = buf;
+    return false;
+  }
+  return true;
+}
+
+int pick_block_n(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
+
+template <int BN>
+cudaError_t launch_gemm_bn(const GemmParams& p, int grid, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, cudaStream_t s) {
+  switch (bn) {
+    case 32: return launch_gemm_bn<32>(p, grid, s);
+    case 64: return launch_gemm_bn<64>(p, grid, s);
+    case 128: return launch_gemm_bn<128>(p, grid, s);
+    default: return launch_gemm_bn<256>(p, grid, s);
+  }
+}
+
+// Description of one spatial GEMM (see gemm_tc.cuh).
+struct GemmOp {
+  const void* A = nullptr;
+  int B = 1, Ht = 1, Wt = 1, C = 0;   // A tensor [B, Ht, Wt, C] (C innermost, dense)
+  int H = 0, W = 0;                   // output / tiling extent (defaults Ht, Wt - xoff)
+  int xoff = 0;
+  const void* Wt_ptr = nullptr;       // [N, taps*kpad] 16-bit
+  int N = 0, taps = 1, kpad = 0;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  int out_kind = OUT_HALF;
+  void* out = nullptr;
+  long long ldo = 0;                  // default N
+  int OH = 0, OW = 0, so = 1, oy = 0, ox = 0;  // default OH = H, OW = W
+  const void* add1 = nullptr;
+  long long ld_add1 = 0;
+  const void* add2 = nullptr;
+  long long ld_add2 = 0;
+  void* out2_relu = nullptr;
+  long long ld_out2 = 0;
+  const float* head_w = nullptr;      // host pointer to 32 floats (OUT_HEAD)
+  float head_b = 0.f;
+  int head_act = ACT_RELU;
+};
+
+bool add_gemm(Ctx& c, GemmOp op) {
+  if (op.H == 0) op.H = op.Ht;
+  if (op.W == 0) op.W = op.Wt - op.xoff;
+  if (op.OH == 0) op.OH = op.H * op.so;
+  if (op.OW == 0) op.OW = op.W * op.so;
+  if (op.ldo == 0) op.ldo = op.N;
+  if (op.kpad == 0) op.kpad = (op.C + 63) / 64 * 64;
+  if (op.C % 8 != 0) return c.fail("gemm: channel count must be a multiple of 8");
+  if (op.out_kind != OUT_HEAD && op.N % 8 != 0) return c.fail("gemm: N must be a multiple of 8");
+  if (c.dry) return true;
+
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  // tile shape: minimise the number of 128-pixel tiles
+  int best_log2 = 7;
+  long long best_tiles = -1;
+  for (int l2 = 7; l2 >= 3; --l2) {
+    const int tw = 1 << l2, th = 128 >> l2;
+    const long long t = (long long)((op.W + tw - 1) / tw) * ((op.H + th - 1) / th);
+    if (best_tiles < 0 || t < best_tiles) { best_tiles = t; best_log2 = l2; }
+  }
+  const int TW = 1 << best_log2, TH = 128 >> best_log2;
+  const int bn = op.out_kind == OUT_HEAD ? 32 : pick_block_n(op.N);
+  if (op.out_kind == OUT_HEAD && op.N != 32) return c.fail("gemm: head mode needs N == 32");
+
+  {
+    uint64_t dims[4] = {(uint64_t)op.C, (uint64_t)op.Wt, (uint64_t)op.Ht, (uint64_t)op.B};
+    uint64_t str[3] = {(uint64_t)op.C * 2, (uint64_t)op.C * 2 * op.Wt, (uint64_t)op.C * 2 * op.Wt * op.Ht};
+    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    if (!make_tmap(&p.tmA, op.A, 4, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
+  }
+  {
+    const uint64_t ktot = (uint64_t)op.taps * op.kpad;
+    uint64_t dims[2] = {ktot, (uint64_t)op.N};
+    uint64_t str[1] = {ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    if (!make_tmap(&p.tmB, op.Wt_ptr, 2, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
+  }
+  p.W = op.W; p.H = op.H; p.B = op.B;
+  p.tw_log2 = best_log2;
+  p.tiles_x = (op.W + TW - 1) / TW;
+  p.tiles_y = (op.H + TH - 1) / TH;
+  p.N = op.N;
+  p.n_tiles = (op.N + bn - 1) / bn;
+  p.num_taps = op.taps;
+  p.kchunks = op.kpad / 64;
+  p.a_xoff = op.xoff;
+  p.is_bf16 = c.is_bf16;
+  p.bias = op.bias;
+  p.act = op.act;
+  p.out_kind = op.out_kind;
+  p.out = op.out;
+  p.ldo = op.ldo;
+  p.OH = op.OH; p.OW = op.OW; p.so = op.so; p.oy = op.oy; p.ox = op.ox;
+  p.add1 = op.add1; p.ld_add1 = op.ld_add1 ? op.ld_add1 : op.ldo;
+  p.add2 = op.add2; p.ld_add2 = op.ld_add2 ? op.ld_add2 : op.ldo;
+  p.out2_relu = op.out2_relu; p.ld_out2 = op.ld_out2 ? op.ld_out2 : op.ldo;
+  if (op.head_w) memcpy(p.head_w, op.head_w, 32 * sizeof(float));
+  p.head_b = op.head_b;
+  p.head_act = op.head_act;
+
+  const long long total = (long long)p.B * p.tiles_y * p.tiles_x * p.n_tiles;
+  const int grid = (int)std::min<long long>(total, c.num_sms);
+  c.launches->push_back([p, bn, grid](cudaStream_t s) { return launch_gemm(p, bn, grid, s); });
+  return true;
+}
+
+bool add_attention(Ctx& c, const void* qkv, const void* bias, void* out, int B, int N, int heads, float scale) {
+  if (c.dry) return true;
+  AttnParams p;
+  memset(&p, 0, sizeof p);
+  const int F = heads * 64;
+  uint64_t dims[3] = {(uint64_t)3 * F, (uint64_t)N, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)3 * F * 2, (uint64_t)3 * F * 2 * N};
+  uint32_t box[3] = {64, 128, 1};
+  if (!make_tmap(&p.tmQKV, qkv, 3, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
+  p.N = N; p.H = heads; p.B = B; p.F = F;
+  p.is_bf16 = c.is_bf16;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = out;
+  p.bias = bias;
+  p.ldb = N;
+  dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
+  c.launches->push_back([p, grid](cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+  });
+  return true;
+}
+
+int ew_grid(long long n, int block, int num_sms) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms * 16;
+  return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+#define DISPATCH_T(is_bf16, ...)                     \
+  do {                                               \
+    if (is_bf16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = __half; __VA_ARGS__; }          \
+  } while (0)
+
+bool add_layernorm(Ctx& c, const float* x, const float* w, const float* b, void* y, long long M, int F, float eps) {
+  if (F % 4 != 0 || F > 1536) return c.fail("layernorm: F must be a multiple of 4 and <= 1536");
+  if (c.dry) return true;
+  const int is_bf16 = c.is_bf16;
+  c.launches->push_back([=](cudaStream_t s) {
+    const int rows_per_block = 8;
+    const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+    DISPATCH_T(is_bf16, (layernorm_kernel<T, float><<<grid, rows_per_block * 32, 0, s>>>(x, w, b, (T*)y, M, F, eps)));
+    return cudaGetLastError();
+  });
+  return true;
+}
+
+bool add_resize(Ctx& c, const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C) {
+  if (C % 8 != 0) return c.fail("resize: C must be a multiple of 8");
+  if (c.dry) return true;
+  const int is_bf16 = c.is_bf16;
+  const int nsm = c.num_sms;
+  c.launches->push_back([=](cudaStream_t s) {
+    const long long total = (long long)B * OH * OW * (C / 8);
+    const int grid = ew_grid(total, 256, nsm);
+    DISPATCH_T(is_bf16, (resize_bilinear_ac_kernel<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, B, IH, IW, OH, OW, C)));
+    return cudaGetLastError();
+  });
+  return true;
+}
+
+bool add_relu_copy(Ctx& c, const void* in, void* out, long long n) {
+  if (n % 8 != 0) return c.fail("relu_copy: size must be a multiple of 8");
+  if (c.dry) return true;
+  const int is_bf16 = c.is_bf16;
+  const int nsm = c.num_sms;
+  c.launches->push_back([=](cudaStream_t s) {
+    const int grid = ew_grid(n / 8, 256, nsm);
+    DISPATCH_T(is_bf16, (relu_copy_kernel<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, n / 8)));
+    return cudaGetLastError();
+  });
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weights
+
+const Weight* get_w(Ctx& c, const std::string& name, int expect_dtype) {
+  auto it = c.m->weights.find(name);
+  if (it == c.m->weights.end()) {
+    c.fail("missing weight: " + name);
+    return nullptr;
+  }
+  if (it->second.dtype != expect_dtype) {
+    c.fail("weight " + name + " has the wrong dtype");
+    return nullptr;
+  }
+  return &it->second;
+}
+int half_dt(const Ctx& c) { return c.is_bf16 ? DPT_BF16 : DPT_F16; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage builders (DINOv2 / Depth-Anything V2)
+
+// PatchEmbed.forward - v2_depthanything/patch_embed.py:77-99
+bool build_patch_embed(Ctx& c, const void* img, void* tokens, int B, int H, int W) {
+  const dpt_config& cfg = c.m->cfg;
+  const int P = cfg.patch_size_px, F = cfg.features_per_token;
+  if (H % P || W % P) return c.fail("image size must be a multiple of the patch size");
+  const int gh = H / P, gw = W / P;
+  const Weight* w = get_w(c, "patch.w", half_dt(c));
+  const Weight* b = get_w(c, "patch.b", DPT_F32);
+  if (!w || !b) return false;
+  const int kpad = (int)w->shape[1];
+  const long long M = (long long)B * gh * gw;
+  const size_t mk = c.ar.mark();
+  void* A = c.ar.alloc((size_t)M * kpad * 2);
+  if (!c.dry) {
+    const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+    c.launches->push_back([=](cudaStream_t s) {
+      const int grid = ew_grid(M * kpad, 256, nsm);
+      DISPATCH_T(is_bf16, (im2col_patch_kernel<T><<<grid, 256, 0, s>>>((const T*)img, (T*)A, B, 3, H, W, P, gh, gw, kpad)));
+      return cudaGetLastError();
+    });
+  }
+  GemmOp op;
+  op.A = A; op.B = 1; op.Ht = 1; op.Wt = (int)M; op.C = kpad;
+  op.Wt_ptr = w->ptr; op.N = F; op.taps = 1; op.kpad = kpad;
+  op.bias = (const float*)b->ptr;
+  op.out = tokens;
+  bool ok = add_gemm(c, op);
+  c.ar.reset(mk);
+  return ok;
+}
+
+// DinoV2Model4Stages.forward - v2_depthanything/image_encoder_model.py:80-94, transformer_block.py:53-65,154-170
+bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int gh, int gw) {
+  const dpt_config& cfg = c.m->cfg;
+  const int F = cfg.features_per_token, heads = cfg.num_heads, L = cfg.num_blocks;
+  if (L % 4 != 0) return c.fail("num_blocks must be a multiple of 4");
+  if (heads * 64 != F) return c.fail("features_per_token must be 64 * num_heads");
+  const int per_stage = L / 4;
+  const int N = gh * gw + 1;
+  const long long M = (long long)B * N;
+  const int hd = half_dt(c);
+  const size_t mk = c.ar.mark();
+  float* pos = (float*)c.ar.alloc((size_t)N * F * 4);
+  float* x = (float*)c.ar.alloc((size_t)M * F * 4);
+  void* ln = c.ar.alloc((size_t)M * F * 2);
+  void* qkv = c.ar.alloc((size_t)M * 3 * F * 2);
+  void* att = c.ar.alloc((size_t)M * F * 2);
+  void* hid = c.ar.alloc((size_t)M * 4 * F * 2);
+
+  const Weight* base = get_w(c, "pos.base", DPT_F32);
+  const Weight* cls_tok = get_w(c, "pos.cls_tok", DPT_F32);
+  const Weight* cls_emb = get_w(c, "pos.cls_emb", DPT_F32);
+  const Weight* on_w = get_w(c, "outnorm.w", DPT_F32);
+  const Weight* on_b = get_w(c, "outnorm.b", DPT_F32);
+  if (!base || !cls_tok || !cls_emb || !on_w || !on_b) return false;
+  if (!c.dry) {
+    const int bh = cfg.base_grid_h, bw = cfg.base_grid_w;
+    const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+    const float *bp = (const float*)base->ptr, *ct = (const float*)cls_tok->ptr, *ce = (const float*)cls_emb->ptr;
+    c.launches->push_back([=](cudaStream_t s) {
+      pos_table_kernel<<<N, 128, 0, s>>>(bp, ct, ce, pos, bh, bw, gh, gw, F);
+      return cudaGetLastError();
+    });
+    c.launches->push_back([=](cudaStream_t s) {
+      const int grid = ew_grid(M * F / 4, 256, nsm);
+      DISPATCH_T(is_bf16, (assemble_tokens_kernel<T><<<grid, 256, 0, s>>>((const T*)tokens, pos, x, B, N, F)));
+      return cudaGetLastError();
+    });
+  }
+  const float scale = 1.0f / sqrtf(64.0f);
+  for (int i = 0; i < L && c.ok; ++i) {
+    const std::string pre = "blk" + std::to_string(i) + ".";
+    const Weight *l1w = get_w(c, pre + "ln1.w", DPT_F32), *l1b = get_w(c, pre + "ln1.b", DPT_F32);
+    const Weight *l2w = get_w(c, pre + "ln2.w", DPT_F32), *l2b = get_w(c, pre + "ln2.b", DPT_F32);
+    const Weight *qw = get_w(c, pre + "qkv.w", hd), *qb = get_w(c, pre + "qkv.b", DPT_F32);
+    const Weight *pw = get_w(c, pre + "proj.w", hd), *pb = get_w(c, pre + "proj.b", DPT_F32);
+    const Weight *f1w = get_w(c, pre + "fc1.w", hd), *f1b = get_w(c, pre + "fc1.b", DPT_F32);
+    const Weight *f2w = get_w(c, pre + "fc2.w", hd), *f2b = get_w(c, pre + "fc2.b", DPT_F32);
+    if (!c.ok) return false;
+    const int hidden = (int)f1w->shape[0];
+    add_layernorm(c, x, (const float*)l1w->ptr, (const float*)l1b->ptr, ln, M, F, cfg.ln_eps);
+    {
+      GemmOp op;
+      op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = qw->ptr; op.N = 3 * F; op.kpad = (int)qw->shape[1];
+      op.bias = (const float*)qb->ptr; op.out = qkv;
+      add_gemm(c, op);
+    }
+    add_attention(c, qkv, nullptr, att, B, N, heads, scale);
+    {
+      GemmOp op;  // x += (gamma1 . proj)(att)   (LayerScale folded into the packed weights)
+      op.A = att; op.Wt = (int)M; op.C = F; op.Wt_ptr = pw->ptr; op.N = F; op.kpad = (int)pw->shape[1];
+      op.bias = (const float*)pb->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x;
+      add_gemm(c, op);
+    }
+    add_layernorm(c, x, (const float*)l2w->ptr, (const float*)l2b->ptr, ln, M, F, cfg.ln_eps);
+    {
+      GemmOp op;
+      op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = hidden; op.kpad = (int)f1w->shape[1];
+      op.bias = (const float*)f1b->ptr; op.act = ACT_GELU; op.out = hid;
+      add_gemm(c, op);
+    }
+    {
+      GemmOp op;
+      op.A = hid; op.Wt = (int)M; op.C = hidden; op.Wt_ptr = f2w->ptr; op.N = F; op.kpad = (int)f2w->shape[1];
+      op.bias = (const float*)f2b->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x;
+      add_gemm(c, op);
+    }
+    if ((i + 1) % per_stage == 0) {
+      const int st = (i + 1) / per_stage - 1;
+      add_layernorm(c, x, (const float*)on_w->ptr, (const float*)on_b->ptr, taps[st], M, F, cfg.ln_eps);
+    }
+  }
+  c.ar.reset(mk);
+  return c.ok;
+}
+
+// ReassembleModel.forward - v2_depthanything/reassembly_model.py:61-94,139-149
+// maps_relu[i] (optional) receives relu(maps[i]) for the fusion stage's first convolutions.
+bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], void* const maps_relu[4], int B, int gh,
+                      int gw) {
+  const dpt_config& cfg = c.m->cfg;
+  const int F = cfg.features_per_token, C = cfg.fusion_channels;
+  if (gh % 2 || gw % 2) return c.fail("patch grid must be even (reference: fusion size mismatch otherwise)");
+  const int N = gh * gw + 1;
+  const int hd = half_dt(c);
+  const size_t mk = c.ar.mark();
+  for (int k = 0; k < 4 && c.ok; ++k) {
+    const int R = cfg.reassembly_features[k];
+    const std::string pre = "reasm" + std::to_string(k) + ".";
+    const Weight *pw = get_w(c, pre + "proj.w", hd), *pb = get_w(c, pre + "proj.b", DPT_F32);
+    const Weight* fw = get_w(c, pre + "fuse.w", hd);
+    if (!c.ok) return false;
+    const size_t mk2 = c.ar.mark();
+    // 1x1 projection on the patch tokens (cls row skipped through the TMA x offset)
+    void* proj = c.ar.alloc((size_t)B * gh * gw * R * 2);
+    {
+      GemmOp op;
+      op.A = taps[k]; op.B = B; op.Ht = 1; op.Wt = N; op.C = F; op.xoff = 1;
+      op.Wt_ptr = pw->ptr; op.N = R; op.kpad = (int)pw->shape[1];
+      op.bias = (const float*)pb->ptr; op.out = proj;
+      add_gemm(c, op);
+    }
+    void* res = proj;
+    int rh = gh, rw = gw;
+    if (k == 0 || k == 1) {
+      // ConvTranspose2d(k = s, stride = s) == s*s GEMMs with pixel-shuffled stores
+      const int s = k == 0 ? 4 : 2;
+      const Weight *uw = get_w(c, pre + "up.w", hd), *ub = get_w(c, pre + "up.b", DPT_F32);
+      if (!c.ok) return false;
+      rh = gh * s; rw = gw * s;
+      res = c.ar.alloc((size_t)B * rh * rw * R * 2);
+      const long long rows_per_sub = uw->shape[0] / (s * s);
+      const int kpad = (int)uw->shape[1];
+      for (int sub = 0; sub < s * s; ++sub) {
+        GemmOp op;
+        op.A = proj; op.B = B; op.Ht = gh; op.Wt = gw; op.C = R;
+        op.Wt_ptr = (const char*)uw->ptr + (size_t)sub * rows_per_sub * kpad * 2;
+        op.N = R; op.kpad = kpad;
+        op.bias = (const float*)ub->ptr; op.out = res;
+        op.so = s; op.oy = sub / s; op.ox = sub % s; op.OH = rh; op.OW = rw;
+        add_gemm(c, op);
+      }
+    } else if (k == 3) {
+      // Conv2d(k=3, s=2, p=1): im2col gather + GEMM
+      const Weight *dw = get_w(c, pre + "down.w", hd), *db = get_w(c, pre + "down.b", DPT_F32);
+      if (!c.ok) return false;
+      rh = gh / 2; rw = gw / 2;
+      const int cpad = (int)dw->shape[1] / 9;
+      void* col = c.ar.alloc((size_t)B * rh * rw * 9 * cpad * 2);
+      res = c.ar.alloc((size_t)B * rh * rw * R * 2);
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+        const void* pin = proj;
+        c.launches->push_back([=](cudaStream_t s) {
+          const long long total = (long long)B * rh * rw * 9 * (cpad / 8);
+          const int grid = ew_grid(total, 256, nsm);
+          DISPATCH_T(is_bf16, (im2col_3x3s2_kernel<T><<<grid, 256, 0, s>>>((const T*)pin, (T*)col, B, gh, gw, R, cpad)));
+          return cudaGetLastError();
+        });
+      }
+      GemmOp op;
+      op.A = col; op.B = 1; op.Ht = 1; op.Wt = B * rh * rw; op.C = 9 * cpad;
+      op.Wt_ptr = dw->ptr; op.N = R; op.kpad = 9 * cpad;
+      op.bias = (const float*)db->ptr; op.out = res;
+      add_gemm(c, op);
+    }
+    {
+      // fuse_proj: 3x3, R -> C, no bias
+      GemmOp op;
+      op.A = res; op.B = B; op.Ht = rh; op.Wt = rw; op.C = R;
+      op.Wt_ptr = fw->ptr; op.N = C; op.taps = 9; op.kpad = (int)fw->shape[1] / 9;
+      op.out = maps[k];
+      op.out2_relu = maps_relu ? maps_relu[k] : nullptr;
+      add_gemm(c, op);
+    }
+    c.ar.reset(mk2);
+  }
+  c.ar.reset(mk);
+  return c.ok;
+}
+
+// FusionModel.forward - v2_depthanything/fusion_model.py:55-80,148-154,159-220
+// The 1x1 output projection is applied before the x2 bilinear upsample (they commute: both are linear and the
+// interpolation weights sum to one), a 4x FLOP saving - SURVEY.md §8a-bis.
+bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu_in[4], void* fused, int B, int gh,
+                  int gw) {
+  const dpt_config& cfg = c.m->cfg;
+  const int C = cfg.fusion_channels;
+  if (gh % 2 || gw % 2) return c.fail("patch grid must be even");
+  const int hd = half_dt(c);
+  const size_t mk = c.ar.mark();
+  const int hs[4] = {gh * 4, gh * 2, gh, gh / 2};
+  const int ws[4] = {gw * 4, gw * 2, gw, gw / 2};
+  const void* f_prev = nullptr;  // previous fusion output, already at this level's resolution
+  void* f_bufs[2] = {nullptr, nullptr};
+  // upsampled outputs ping-pong between two buffers sized for the largest consumer (level 0 input = 4g) ; the final
+  // one goes to `fused`.
+  f_bufs[0] = c.ar.alloc((size_t)B * hs[0] * ws[0] * C * 2);
+  f_bufs[1] = c.ar.alloc((size_t)B * hs[0] * ws[0] * C * 2);
+  const size_t big = (size_t)B * hs[0] * ws[0] * C * 2;
+  void* t_buf = c.ar.alloc(big);
+  void* t_relu = c.ar.alloc(big);
+  void* a_relu = c.ar.alloc(big);
+  void* v_buf = c.ar.alloc(big);
+  void* w_buf = c.ar.alloc(big);
+  void* r_relu_tmp = c.ar.alloc(big);
+  for (int lvl = 3; lvl >= 0 && c.ok; --lvl) {
+    const int h = hs[lvl], w = ws[lvl];
+    const std::string pre = "fus" + std::to_string(lvl) + ".";
+    const void* r = maps[lvl];
+    const void* r_relu = maps_relu_in ? maps_relu_in[lvl] : nullptr;
+    if (!r_relu) {
+      add_relu_copy(c, r, r_relu_tmp, (long long)B * h * w * C);
+      r_relu = r_relu_tmp;
+    }
+    auto conv3 = [&](const void* in, const std::string& wn, int act, void* out, const void* add1, const void* add2,
+                     void* out_relu) {
+      const Weight *ww = get_w(c, wn + ".w", hd), *bb = get_w(c, wn + ".b", DPT_F32);
+      if (!c.ok) return;
+      GemmOp op;
+      op.A = in; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
+      op.Wt_ptr = ww->ptr; op.N = C; op.taps = 9; op.kpad = (int)ww->shape[1] / 9;
+      op.bias = (const float*)bb->ptr; op.act = act; op.out = out; op.add1 = add1; op.add2 = add2;
+      op.out2_relu = out_relu;
+      add_gemm(c, op);
+    };
+    const void* t = r;
+    const void* tr = r_relu;
+    if (lvl < 3) {
+      // conv_reassembly (ResidualConv2D) + previous fusion
+      conv3(r_relu, pre + "rcu1.c1", ACT_RELU, a_relu, nullptr, nullptr, nullptr);
+      conv3(a_relu, pre + "rcu1.c2", ACT_NONE, t_buf, r, f_prev, t_relu);
+      t = t_buf;
+      tr = t_relu;
+    }
+    // scale_proj_seq: ResidualConv2D -> (1x1 projection, x2 upsample)
+    conv3(tr, pre + "rcu2.c1", ACT_RELU, a_relu, nullptr, nullptr, nullptr);
+    conv3(a_relu, pre + "rcu2.c2", ACT_NONE, v_buf, t, nullptr, nullptr);
+    {
+      const Weight *ww = get_w(c, pre + "out.w", hd), *bb = get_w(c, pre + "out.b", DPT_F32);
+      if (!c.ok) return false;
+      GemmOp op;
+      op.A = v_buf; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
+      op.Wt_ptr = ww->ptr; op.N = C; op.taps = 1; op.kpad = (int)ww->shape[1];
+      op.bias = (const float*)bb->ptr; op.out = w_buf;
+      add_gemm(c, op);
+    }
+    void* up = lvl == 0 ? fused : f_bufs[lvl & 1];
+    add_resize(c, w_buf, up, B, h, w, 2 * h, 2 * w, C);
+    f_prev = up;
+  }
+  c.ar.reset(mk);
+  return c.ok;
+}
+
+// MonocularDepthHead.forward - v2_depthanything/head_model.py:61-106
+bool build_head(Ctx& c, const void* fused, void* depth, int B, int gh, int gw) {
+  const dpt_config& cfg = c.m->cfg;
+  const int C = cfg.fusion_channels, P = cfg.patch_size_px;
+  const int hd = half_dt(c);
+  const int h = gh * 8, w = gw * 8;
+  // F.interpolate(scale_factor = P / 8): output size floor(in * scale)
+  const int OH = (int)floor((double)h * ((double)P / 8.0)), OW = (int)floor((double)w * ((double)P / 8.0));
+  const Weight *w1 = get_w(c, "head.c1.w", hd), *b1 = get_w(c, "head.c1.b", DPT_F32);
+  const Weight *w2 = get_w(c, "head.c2.w", hd), *b2 = get_w(c, "head.c2.b", DPT_F32);
+  const Weight *w3 = get_w(c, "head.c3.w_host", DPT_F32), *b3 = get_w(c, "head.c3.b_host", DPT_F32);
+  if (!c.ok) return false;
+  const int C2 = (int)w1->shape[0];
+  const size_t mk = c.ar.mark();
+  void* h1 = c.ar.alloc((size_t)B * h * w * C2 * 2);
+  void* h2 = c.ar.alloc((size_t)B * OH * OW * C2 * 2);
+  {
+    GemmOp op;
+    op.A = fused; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
+    op.Wt_ptr = w1->ptr; op.N = C2; op.taps = 9; op.kpad = (int)w1->shape[1] / 9;
+    op.bias = (const float*)b1->ptr; op.out = h1;
+    add_gemm(c, op);
+  }
+  add_resize(c, h1, h2, B, h, w, OH, OW, C2);
+  {
+    GemmOp op;
+    op.A = h2; op.B = B; op.Ht = OH; op.Wt = OW; op.C = C2;
+    op.Wt_ptr = w2->ptr; op.N = 32; op.taps = 9; op.kpad = (int)w2->shape[1] / 9;
+    op.bias = (const float*)b2->ptr; op.out_kind = OUT_HEAD; op.out = depth; op.ldo = 1;
+    op.head_w = (const float*)w3->ptr;        // host memory (see dpt_set_weight: "*_host" names are copied)
+    op.head_b = *(const float*)b3->ptr;
+    op.head_act = cfg.is_metric ? ACT_SIGMOID : ACT_RELU;
+    add_gemm(c, op);
+  }
+  c.ar.reset(mk);
+  return c.ok;
+}
+
+struct FwdBuffers {
+  void* tokens;
+  void* taps[4];
+  void* maps[4];
+  void* maps_relu[4];
+  void* fused;
+};
+
+bool build_forward(Ctx& c, const void* img, void* depth, int B, int H, int W) {
+  const dpt_config& cfg = c.m->cfg;
+  const int P = cfg.patch_size_px, F = cfg.features_per_token, C = cfg.fusion_channels;
+  if (H % P || W % P) return c.fail("image height/width must be multiples of the patch size");
+  const int gh = H / P, gw = W / P;
+  if (gh % 2 || gw % 2)
+    return c.fail("patch grid must be even in both directions (the reference raises inside fusion for odd grids)");
+  const int N = gh * gw + 1;
+  FwdBuffers fb;
+  fb.tokens = c.ar.alloc((size_t)B * gh * gw * F * 2);
+  for (int k = 0; k < 4; ++k) fb.taps[k] = c.ar.alloc((size_t)B * N * F * 2);
+  const int hs[4] = {gh * 4, gh * 2, gh, gh / 2}, ws[4] = {gw * 4, gw * 2, gw, gw / 2};
+  for (int k = 0; k < 4; ++k) {
+    fb.maps[k] = c.ar.alloc((size_t)B * hs[k] * ws[k] * C * 2);
+    fb.maps_relu[k] = c.ar.alloc((size_t)B * hs[k] * ws[k] * C * 2);
+  }
+  fb.fused = c.ar.alloc((size_t)B * gh * 8 * gw * 8 * C * 2);
+  if (!build_patch_embed(c, img, fb.tokens, B, H, W)) return false;
+  if (!build_encoder(c, fb.tokens, fb.taps, B, gh, gw)) return false;
+  if (!build_reassemble(c, fb.taps, fb.maps, fb.maps_relu, B, gh, gw)) return false;
+  if (!build_fusion(c, fb.maps, fb.maps_relu, fb.fused, B, gh, gw)) return false;
+  if (!build_head(c, fb.fused, depth, B, gh, gw)) return false;
+  return c.ok;
+}
+
+Ctx make_ctx(dpt_model_s* m, void* ws, size_t ws_bytes, std::vector<LaunchFn>* launches, bool dry) {
+  Ctx c;
+  c.m = m;
+  c.ar.base = (char*)ws;
+  c.ar.cap = ws_bytes;
+  c.ar.dry = dry;
+  c.launches = launches;
+  c.dry = dry;
+  c.is_bf16 = m ? (m->cfg.dtype == DPT_BF16) : 1;
+  c.num_sms = m ? m->num_sms : 148;
+  return c;
+}
+
+int run_launches(dpt_model_s* m, std::vector<LaunchFn>& launches, cudaStream_t s, std::string& err) {
+  int n = 0;
+  for (auto& f : launches) {
+    cudaError_t e = f(s);
+    if (e != cudaSuccess) {
+      err = std::string("kernel launch failed: ") + cudaGetErrorString(e);
+      return DPT_ERR_CUDA;
+    }
+    ++n;
+  }
+  if (m) m->last_launches = n;
+  return DPT_OK;
+}
+
+template <typename BuildFn>
+int build_and_run(dpt_model_s* h, void* ws, size_t ws_bytes, void* stream, BuildFn&& fn) {
+  if (!h) return DPT_ERR_INVALID;
+  std::vector<LaunchFn> launches;
+  Ctx c = make_ctx(h, ws, ws_bytes, &launches, false);
+  if (!fn(c)) {
+    h->err = c.err;
+    return c.err.rfind("missing weight", 0) == 0 ? DPT_ERR_MISSING : DPT_ERR_INVALID;
+  }
+  if (c.ar.overflow) {
+    h->err = "workspace too small: need " + std::to_string(c.ar.peak) + " bytes";
+    return DPT_ERR_WORKSPACE;
+  }
+  return run_launches(h, launches, (cudaStream_t)stream, h->err);
+}
+
+}  // namespace
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+
+extern "C" {
+
+const char* dpt_version(void) { return "dpt_b200 0.1 (sm_100a)"; }
+
+int dpt_create(const dpt_config* cfg, dpt_handle* out) {
+  if (!cfg || !out) { g_err = "null argument"; return DPT_ERR_INVALID; }
+  if (cfg->variant != DPT_VARIANT_DINOV2) { g_err = "variant not supported by this build"; return DPT_ERR_UNSUPPORTED; }
+  if (cfg->dtype != DPT_BF16 && cfg->dtype != DPT_F16) { g_err = "dtype must be fp16 or bf16"; return DPT_ERR_INVALID; }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { g_err = std::string("cudaGetDevice: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { g_err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_err = "libdpt_b200 requires an sm_100 (Blackwell B200) device; found sm_" + std::to_string(prop.major) +
+            std::to_string(prop.minor);
+    return DPT_ERR_UNSUPPORTED;
+  }
+  dpt_model_s* m = new dpt_model_s();
+  m->cfg = *cfg;
+  m->num_sms = prop.multiProcessorCount;
+  m->device = dev;
+  *out = m;
+  return DPT_OK;
+}
+
+void dpt_destroy(dpt_handle h) { delete h; }
+
+const char* dpt_last_error(dpt_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+const char* dpt_op_last_error(void) { return g_err.c_str(); }
+int dpt_last_launch_count(dpt_handle h) { return h ? h->last_launches : 0; }
+
+int dpt_set_weight(dpt_handle h, const char* name, const void* dev_ptr, const int64_t* shape, int ndim, int dtype) {
+  if (!h || !name || !dev_ptr || ndim < 0 || ndim > 4) return DPT_ERR_INVALID;
+  Weight w;
+  w.ptr = dev_ptr;
+  w.ndim = ndim;
+  w.dtype = dtype;
+  for (int i = 0; i < ndim; ++i) w.shape[i] = shape[i];
+  const std::string nm(name);
+  if (nm.size() > 5 && nm.compare(nm.size() - 5, 5, "_host") == 0) {
+    // host-resident fp32 vector: copied into the handle (used as kernel parameters, e.g. the head's 32->1 weights)
+    if (dtype != DPT_F32) { h->err = "host weights must be f32"; return DPT_ERR_INVALID; }
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    std::vector<float>& v = h->host_copies[nm];
+    v.assign((const float*)dev_ptr, (const float*)dev_ptr + n);
+    w.ptr = v.data();
+  }
+  h->weights[name] = w;
+  h->fwd_plan.valid = false;
+  return DPT_OK;
+}
+
+int dpt_workspace_bytes(dpt_handle h, int B, int H, int W, size_t* bytes) {
+  if (!h || !bytes) return DPT_ERR_INVALID;
+  Ctx c = make_ctx(h, nullptr, 0, nullptr, true);
+  if (!build_forward(c, nullptr, nullptr, B, H, W)) {
+    h->err = c.err;
+    return c.err.rfind("missing weight", 0) == 0 ? DPT_ERR_MISSING : DPT_ERR_INVALID;
+  }
+  *bytes = c.ar.peak + 1024;
+  return DPT_OK;
+}
+
+int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_bytes, int B, int H, int W,
+                void* stream) {
+  if (!h || !img || !depth || !ws) return DPT_ERR_INVALID;
+  Plan& pl = h->fwd_plan;
+  if (!(pl.valid && pl.img == img && pl.out == depth && pl.ws == ws && pl.B == B && pl.H == H && pl.W == W)) {
+    pl.valid = false;
+    pl.launches.clear();
+    Ctx c = make_ctx(h, ws, ws_bytes, &pl.launches, false);
+    if (!build_forward(c, img, depth, B, H, W)) {
+      h->err = c.err;
+      return c.err.rfind("missing weight", 0) == 0 ? DPT_ERR_MISSING : DPT_ERR_INVALID;
+    }
+    if (c.ar.overflow) {
+      h->err = "workspace too small: need " + std::to_string(c.ar.peak) + " bytes";
+      return DPT_ERR_WORKSPACE;
+    }
+    pl.img = img; pl.out = depth; pl.ws = ws; pl.B = B; pl.H = H; pl.W = W;
+    pl.valid = true;
+  }
+  return run_launches(h, pl.launches, (cudaStream_t)stream, h->err);
+}
+
+int dpt_forward_host(dpt_handle h, const void* host_img, void* host_depth, void* dev_img, void* dev_depth, void* ws,
+                     size_t ws_bytes, int B, int H, int W, void* stream) {
+  if (!h || !host_img || !host_depth || !dev_img || !dev_depth) return DPT_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(dev_img, host_img, (size_t)B * 3 * H * W * 2, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { h->err = std::string("H2D copy: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
+  int rc = dpt_forward(h, dev_img, dev_depth, ws, ws_bytes, B, H, W, stream);
+  if (rc != DPT_OK) return rc;
+  e = cudaMemcpyAsync(host_depth, dev_depth, (size_t)B * H * W * 2, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) { h->err = std::string("D2H copy: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { h->err = std::string("stream sync: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
+  return DPT_OK;
+}
+
+int dpt_patch_embed(dpt_handle h, const void* img, void* tokens, void* ws, size_t ws_bytes, int B, int H, int W,
+                    void* stream) {
+  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) { return build_patch_embed(c, img, tokens, B, H, W); });
+}
+int dpt_encoder(dpt_handle h, const void* tokens, void* const taps[4], void* ws, size_t ws_bytes, int B, int gh, int gw,
+                void* stream) {
+  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) { return build_encoder(c, tokens, taps, B, gh, gw); });
+}
+int dpt_reassemble(dpt_handle h, const void* const taps[4], void* const maps[4], void* ws, size_t ws_bytes, int B,
+                   int gh, int gw, void* stream) {
+  return build_and_run(h, ws, ws_bytes, stream,
+                       [&](Ctx& c) { return build_reassemble(c, taps, maps, nullptr, B, gh, gw); });
+}
+int dpt_fusion(dpt_handle h, const void* const maps[4], void* fused, void* ws, size_t ws_bytes, int B, int gh, int gw,
+               void* stream) {
+  return build_and_run(h, ws, ws_bytes, stream,
+                       [&](Ctx& c) { return build_fusion(c, maps, nullptr, fused, B, gh, gw); });
+}
+int dpt_head(dpt_handle h, const void* fused, void* depth, void* ws, size_t ws_bytes, int B, int gh, int gw,
+             void* stream) {
+  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) { return build_head(c, fused, depth, B, gh, gw); });
+}
+
+// ------------------------------------------------------- single operators ---------------------------------------
+
+static int run_op(Ctx& c, std::vector<LaunchFn>& launches, void* stream) {
+  if (!c.ok) { g_err = c.err; return DPT_ERR_INVALID; }
+  std::string err;
+  int rc = run_launches(nullptr, launches, (cudaStream_t)stream, err);
+  if (rc != DPT_OK) g_err = err;
+  return rc;
+}
+
+int dpt_op_conv_gemm(const void* A, const void* Wt, const float* bias, void* out, const void* add1, const void* add2,
+                     void* out_relu, int B, int H, int W, int C, int N, int taps, int xoff, int act, int out_f32,
+                     int dtype, void* stream) {
+  std::vector<LaunchFn> launches;
+  Ctx c = make_ctx(nullptr, nullptr, 0, &launches, false);
+  c.is_bf16 = dtype == DPT_BF16;
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  c.num_sms = nsm;
+  GemmOp op;
+  op.A = A; op.B = B; op.Ht = H; op.Wt = W; op.C = C; op.xoff = xoff;
+  op.Wt_ptr = Wt; op.N = N; op.taps = taps;
+  op.bias = bias; op.act = act; op.out_kind = out_f32 ? OUT_F32 : OUT_HALF;
+  op.out = out; op.add1 = add1; op.add2 = add2; op.out2_relu = out_relu;
+  add_gemm(c, op);
+  return run_op(c, launches, stream);
+}
+
+int dpt_op_attention(const void* qkv, const void* bias, void* out, int B, int N, int heads, float scale, int dtype,
+                     void* stream) {
+  std::vector<LaunchFn> launches;
+  Ctx c = make_ctx(nullptr, nullptr, 0, &launches, false);
+  c.is_bf16 = dtype == DPT_BF16;
+  add_attention(c, qkv, bias, out, B, N, heads, scale);
+  return run_op(c, launches, stream);
+}
+
+int dpt_op_layernorm(const float* x, const float* w, const float* b, void* y, int64_t M, int F, float eps, int dtype,
+                     void* stream) {
+  std::vector<LaunchFn> launches;
+  Ctx c = make_ctx(nullptr, nullptr, 0, &launches, false);
+  c.is_bf16 = dtype == DPT_BF16;
+  add_layernorm(c, x, w, b, y, M, F, eps);
+  return run_op(c, launches, stream);
+}
+
+int dpt_op_resize_bilinear(const void* in, void* out, int B, int IH, int IW, int OH, int OW, int C, int dtype,
+                           void* stream) {
+  std::vector<LaunchFn> launches;
+  Ctx c = make_ctx(nullptr, nullptr, 0, &launches, false);
+  c.is_bf16 = dtype == DPT_BF16;
+  add_resize(c, in, out, B, IH, IW, OH, OW, C);
+  return run_op(c, launches, stream);
+}
+
+}  // extern "C"

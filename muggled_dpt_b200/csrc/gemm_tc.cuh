@@ -1,0 +1,390 @@
+// "Spatial GEMM": the one tensor-core kernel behind every Linear / 1x1 / 3x3 / ConvTranspose(k=s) layer of the DPT
+// hot path (SURVEY.md §2.2 K1,K4,K6-K8,K10-K14,K16,K17,K19).
+//
+//   out[pixel(b,y,x), n] = epilogue( sum_{tap} sum_{c} A[b, y+dy(tap), x+dx(tap)+xoff, c] * Wt[n, tap*kpad + c] )
+//
+// * A is a channels-last activation tensor seen through a 4-D TMA tensor map (C, W, H, B). One M-tile is a
+//   TH x TW patch of 128 pixels of one image; a 3x3 convolution is nine shifted TMA loads of the same patch
+//   (out-of-bounds rows/columns are zero-filled by the TMA unit == zero padding). Token matrices [M, K] are the
+//   degenerate case H = 1, TW = 128; "drop the cls token" is xoff = 1 on a (F, N, 1, B) map.
+// * Wt is [N, taps*kpad] K-major (nn.Linear / packed conv weights), loaded by a 2-D TMA map.
+// * tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16, bf16/fp16 -> fp32) accumulates in TMEM, double-buffered so
+//   the epilogue of tile i overlaps the main loop of tile i+1. Persistent CTAs, static round-robin tile schedule.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two warpgroups, each
+//   owning half of the accumulator columns; a warp can only read TMEM lanes 32*(warp%4)..+31).
+// * Epilogue: TMEM -> regs -> (+bias, GELU/ReLU) -> swizzled smem staging -> coalesced 16-byte global IO with optional
+//   residual / skip addends, optional second ReLU'd copy, fp32 or 16-bit output, output pixel remap
+//   (y*so+oy, x*so+ox) for pixel-shuffle (ConvTranspose) stores; "head" mode reduces 32 channels to one depth value.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "ptx.cuh"
+
+namespace dpt {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_STAGE_BYTES_PER_WARP = 4096;  // 32 rows x 128 B
+
+enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+enum : int { OUT_HALF = 0, OUT_F32 = 1, OUT_HEAD = 2 };
+
+struct __align__(64) GemmParams {
+  CUtensorMap tmA;  // 4-D (C, W, H, B), box (64, TW, TH, 1), 128B swizzle
+  CUtensorMap tmB;  // 2-D (taps*kpad, N), box (64, BLOCK_N), 128B swizzle
+  int W, H, B;      // input spatial extent used for M tiling (and output-row validity)
+  int tw_log2;      // TW = 1 << tw_log2, TH = 128 >> tw_log2
+  int tiles_x, tiles_y;
+  int N, n_tiles;
+  int num_taps;     // 1 (1x1 / linear) or 9 (3x3, pad 1)
+  int kchunks;      // 64-wide K chunks per tap
+  int a_xoff;       // added to the x coordinate of every A load (token mode: 1 skips the cls row)
+  int is_bf16;      // 16-bit type of A / Wt / 16-bit outputs: 1 = bf16, 0 = fp16
+  // epilogue
+  const float* bias;  // [N] or null
+  int act;
+  int out_kind;
+  void* out;
+  long long ldo;      // elements between consecutive output pixels
+  int OH, OW, so, oy, ox;
+  const void* add1;   // same dtype + pixel indexing as out (may alias out: in-place residual)
+  long long ld_add1;
+  const void* add2;
+  long long ld_add2;
+  void* out2_relu;    // optional second output relu(result), 16-bit, same pixel indexing
+  long long ld_out2;
+  float head_w[32];   // OUT_HEAD: depth = act2(relu(acc + bias) . head_w + head_b)
+  float head_b;
+  int head_act;       // ACT_RELU or ACT_SIGMOID
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+};
+
+DPT_DEVICE float gelu_erf(float x) {
+  // exact-erf GELU (nn.GELU default): 0.5 x (1 + erf(x / sqrt 2)). erf via Abramowitz-Stegun 7.1.28
+  // (|err| < 3e-7): erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, z >= 0.
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float p = fmaf(z, 0.0000430638f, 0.0002765672f);
+  p = fmaf(z, p, 0.0001520143f);
+  p = fmaf(z, p, 0.0092705272f);
+  p = fmaf(z, p, 0.0422820123f);
+  p = fmaf(z, p, 0.0705230784f);
+  p = fmaf(z, p, 1.0f);
+  p = p * p;
+  p = p * p;
+  p = p * p;
+  p = p * p;
+  const float e = 1.0f - __frcp_rn(p);  // erf(|x|/sqrt2)
+  const float half_x = 0.5f * x;
+  return fmaf(copysignf(e, x), half_x, half_x);
+}
+
+DPT_DEVICE float apply_act(float v, int act) {
+  if (act == ACT_GELU) return gelu_erf(v);
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-v));
+  return v;
+}
+
+DPT_DEVICE uint32_t pack2(float a, float b, int is_bf16) {
+  if (is_bf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+DPT_DEVICE float2 unpack2(uint32_t u, int is_bf16) {
+  if (is_bf16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* staging = smem_b + STAGES * Cfg::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int num_kb = p.num_taps * p.kchunks;
+
+  if (warp_idx == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int TW = 1 << p.tw_log2, TH = GEMM_BLOCK_M >> p.tw_log2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int tx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int b = mt / p.tiles_y;
+        const int x0 = tx * TW + p.a_xoff, y0 = ty * TH;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int dy = p.num_taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = p.num_taps == 9 ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+            tma_load_4d(smem_a + s * Cfg::A_BYTES, &p.tmA, &full_bar[s], kc * GEMM_BLOCK_K, x0 + dx, y0 + dy, b);
+            tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], (tap * p.kchunks + kc) * GEMM_BLOCK_K,
+                        n_blk * BLOCK_N);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer =====================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, BLOCK_N, p.is_bf16 != 0, false, false);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES));
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue =====================================
+    const int ew = warp_idx - 2;      // 0..7
+    const int q = warp_idx & 3;       // TMEM lane quarter this warp may read
+    const int wg = ew >> 2;           // column half
+    constexpr int COLS_PER_WG = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
+    const bool wg_active = (BLOCK_N >= 64) || (wg == 0);
+    uint8_t* stg = staging + ew * GEMM_STAGE_BYTES_PER_WARP;
+    const int TW = 1 << p.tw_log2, TH = GEMM_BLOCK_M >> p.tw_log2;
+    const int is_bf16 = p.is_bf16;
+    const int r = q * 32 + lane;  // accumulator row (TMEM lane) owned by this thread
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int n_blk = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int b = mt / p.tiles_y;
+      // output pixel of my row
+      const int x = tx * TW + (r & (TW - 1));
+      const int y = ty * TH + (r >> p.tw_log2);
+      const bool row_ok = (x < p.W) && (y < p.H);
+      const long long pix = ((long long)b * p.OH + (long long)y * p.so + p.oy) * p.OW + (long long)x * p.so + p.ox;
+
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+
+      if (wg_active) {
+        const int col_base = wg * COLS_PER_WG;  // within the tile
+        if (p.out_kind == OUT_HEAD) {
+          if constexpr (BLOCK_N == 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N, v);
+            tmem_ld_wait();
+            float acc = p.head_b;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.0f);
+              acc = fmaf(fmaxf(t, 0.0f), p.head_w[j], acc);
+            }
+            acc = apply_act(acc, p.head_act);
+            if (row_ok) {
+              if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.ldo] = __float2bfloat16_rn(acc);
+              else reinterpret_cast<__half*>(p.out)[pix * p.ldo] = __float2half_rn(acc);
+            }
+          }
+        } else {
+          const bool f32out = p.out_kind == OUT_F32;
+          // staging chunk = 128 B per row: 64 16-bit columns or 32 fp32 columns
+          const int cols_per_stg = f32out ? 32 : 64;
+          for (int c0 = 0; c0 < COLS_PER_WG; c0 += cols_per_stg) {
+            const int ncols_here = min(cols_per_stg, COLS_PER_WG - c0);
+            // ---- phase 1: my row, ncols_here columns -> staging (swizzled 16-byte chunks)
+#pragma unroll 1
+            for (int cc = 0; cc < ncols_here; cc += 32) {
+              const int tcol = col_base + c0 + cc;
+              uint32_t v[32];
+              tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + tcol, v);
+              tmem_ld_wait();
+              const int ncol = n_blk * BLOCK_N + tcol;
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float t = __uint_as_float(v[j]);
+                if (p.bias != nullptr && ncol + j < p.N) t += __ldg(p.bias + ncol + j);
+                f[j] = apply_act(t, p.act);
+              }
+              if (f32out) {
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                  const int phys = ch ^ (lane & 7);
+                  float4 o = make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
+                  *reinterpret_cast<float4*>(stg + lane * 128 + phys * 16) = o;
+                }
+              } else {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                  const int lch = (cc >> 3) + ch;  // logical 16-byte chunk within the 128-byte row
+                  const int phys = lch ^ (lane & 7);
+                  uint4 o;
+                  o.x = pack2(f[8 * ch + 0], f[8 * ch + 1], is_bf16);
+                  o.y = pack2(f[8 * ch + 2], f[8 * ch + 3], is_bf16);
+                  o.z = pack2(f[8 * ch + 4], f[8 * ch + 5], is_bf16);
+                  o.w = pack2(f[8 * ch + 6], f[8 * ch + 7], is_bf16);
+                  *reinterpret_cast<uint4*>(stg + lane * 128 + phys * 16) = o;
+                }
+              }
+            }
+            __syncwarp();
+            // ---- phase 2: coalesced global IO; 8 lanes cover one 128-byte row segment, 4 rows per pass
+            const int ncol0 = n_blk * BLOCK_N + col_base + c0;  // first output column of this staging chunk
+            const int sub = lane & 7;                           // 16-byte chunk within the row segment
+            const int elems_per_chunk = f32out ? 4 : 8;
+            const bool col_ok = (sub * elems_per_chunk < ncols_here) && (ncol0 + sub * elems_per_chunk) < p.N;
+#pragma unroll 1
+            for (int rr0 = 0; rr0 < 32; rr0 += 4) {
+              const int rr = rr0 + (lane >> 3);
+              const long long rpix = __shfl_sync(0xffffffffu, pix, rr);
+              const int rok = __shfl_sync(0xffffffffu, (int)row_ok, rr);
+              if (rok && col_ok) {
+                const int phys = sub ^ (rr & 7);
+                uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + phys * 16);
+                const long long coff = ncol0 + sub * elems_per_chunk;
+                if (f32out) {
+                  float4 o = *reinterpret_cast<float4*>(&val);
+                  if (p.add1) {
+                    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add1) +
+                                                                      rpix * p.ld_add1 + coff);
+                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                  }
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + rpix * p.ldo + coff) = o;
+                } else {
+                  if (p.add1 || p.add2 || p.out2_relu) {
+                    float2 f0 = unpack2(val.x, is_bf16), f1 = unpack2(val.y, is_bf16);
+                    float2 f2 = unpack2(val.z, is_bf16), f3 = unpack2(val.w, is_bf16);
+                    if (p.add1) {
+                      const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add1) +
+                                                                      rpix * p.ld_add1 + coff);
+                      float2 g;
+                      g = unpack2(a.x, is_bf16); f0.x += g.x; f0.y += g.y;
+                      g = unpack2(a.y, is_bf16); f1.x += g.x; f1.y += g.y;
+                      g = unpack2(a.z, is_bf16); f2.x += g.x; f2.y += g.y;
+                      g = unpack2(a.w, is_bf16); f3.x += g.x; f3.y += g.y;
+                    }
+                    if (p.add2) {
+                      const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add2) +
+                                                                      rpix * p.ld_add2 + coff);
+                      float2 g;
+                      g = unpack2(a.x, is_bf16); f0.x += g.x; f0.y += g.y;
+                      g = unpack2(a.y, is_bf16); f1.x += g.x; f1.y += g.y;
+                      g = unpack2(a.z, is_bf16); f2.x += g.x; f2.y += g.y;
+                      g = unpack2(a.w, is_bf16); f3.x += g.x; f3.y += g.y;
+                    }
+                    val.x = pack2(f0.x, f0.y, is_bf16);
+                    val.y = pack2(f1.x, f1.y, is_bf16);
+                    val.z = pack2(f2.x, f2.y, is_bf16);
+                    val.w = pack2(f3.x, f3.y, is_bf16);
+                    if (p.out2_relu) {
+                      uint4 rv;
+                      rv.x = pack2(fmaxf(f0.x, 0.f), fmaxf(f0.y, 0.f), is_bf16);
+                      rv.y = pack2(fmaxf(f1.x, 0.f), fmaxf(f1.y, 0.f), is_bf16);
+                      rv.z = pack2(fmaxf(f2.x, 0.f), fmaxf(f2.y, 0.f), is_bf16);
+                      rv.w = pack2(fmaxf(f3.x, 0.f), fmaxf(f3.y, 0.f), is_bf16);
+                      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2_relu) + rpix * p.ld_out2 + coff) = rv;
+                    }
+                  }
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + rpix * p.ldo + coff) = val;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace dpt

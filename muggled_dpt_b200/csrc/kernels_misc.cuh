@@ -1,0 +1,238 @@
+// HBM-bound helper kernels of the DPT hot path: im2col gathers, token assembly, LayerNorm, bilinear / bicubic
+// resampling, ReLU copy. All activations are channels-last; 16-bit type T is __nv_bfloat16 or __half.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+
+namespace dpt {
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T> struct Vec8 { T v[8]; };  // 16 bytes
+
+// ---------------------------------------------------------------------------------------------------------------
+// Patch-embed im2col (patch_embed.py:92-97): img [B,3,H,W] -> A [B*gh*gw, kpad], k = c*P*P + ky*P + kx, zero padded.
+template <typename T>
+__global__ void im2col_patch_kernel(const T* __restrict__ img, T* __restrict__ A, int B, int Cin, int H, int W, int P,
+                                    int gh, int gw, int kpad) {
+  const long long total = (long long)B * gh * gw * kpad;
+  const int kreal = Cin * P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % kpad);
+    const long long m = idx / kpad;
+    T v = from_f32<T>(0.0f);
+    if (k < kreal) {
+      const int c = k / (P * P);
+      const int rem = k - c * P * P;
+      const int ky = rem / P, kx = rem - ky * P;
+      const int px = (int)(m % gw);
+      const long long t = m / gw;
+      const int py = (int)(t % gh);
+      const int b = (int)(t / gh);
+      v = img[(((long long)b * Cin + c) * H + (py * P + ky)) * W + (px * P + kx)];
+    }
+    A[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 stride-2 pad-1 im2col on NHWC (reassembly_model.py:302-309): in [B,H,W,C] -> A [B*(H/2)*(W/2), 9*cpad],
+// k = tap*cpad + c, tap = ky*3 + kx. 8 channels (16 B) per thread.
+template <typename T>
+__global__ void im2col_3x3s2_kernel(const T* __restrict__ in, T* __restrict__ A, int B, int H, int W, int C, int cpad) {
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const int cv = cpad / 8;
+  const long long total = (long long)B * OH * OW * 9 * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    long long t = idx / cv;
+    const int tap = (int)(t % 9);
+    t /= 9;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    const int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W && c8 * 8 < C)
+      v = *reinterpret_cast<const uint4*>(in + (((long long)b * H + iy) * W + ix) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(A + ((((long long)b * OH + oy) * OW + ox) * 9 + tap) * cpad + c8 * 8) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Position table (position_encoder.py:55-76,108-143): pos[0,:] = cls_token + cls_embedding;
+// pos[1 + y*gw + x, :] = bicubic(base[bh,bw,F]) at (y,x), align_corners=False, A=-0.75, fp32.
+__device__ __forceinline__ float cubic_w1(float x, float A) { return ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f; }
+__device__ __forceinline__ float cubic_w2(float x, float A) { return ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A; }
+
+__global__ void pos_table_kernel(const float* __restrict__ base, const float* __restrict__ cls_tok,
+                                 const float* __restrict__ cls_emb, float* __restrict__ pos, int bh, int bw, int gh,
+                                 int gw, int F) {
+  const int row = blockIdx.x;  // 0 .. gh*gw
+  if (row == 0) {
+    for (int f = threadIdx.x; f < F; f += blockDim.x) pos[f] = cls_tok[f] + cls_emb[f];
+    return;
+  }
+  const int y = (row - 1) / gw, x = (row - 1) % gw;
+  const float A = -0.75f;
+  const float sy = (float)bh / (float)gh, sx = (float)bw / (float)gw;
+  const float fy = sy * (y + 0.5f) - 0.5f, fx = sx * (x + 0.5f) - 0.5f;
+  const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+  const float ty = fy - iy, tx = fx - ix;
+  float wy[4] = {cubic_w2(ty + 1.0f, A), cubic_w1(ty, A), cubic_w1(1.0f - ty, A), cubic_w2(2.0f - ty, A)};
+  float wx[4] = {cubic_w2(tx + 1.0f, A), cubic_w1(tx, A), cubic_w1(1.0f - tx, A), cubic_w2(2.0f - tx, A)};
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), bh - 1);
+      float racc = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int xx = min(max(ix - 1 + c, 0), bw - 1);
+        racc += wx[c] * base[((long long)yy * bw + xx) * F + f];
+      }
+      acc += wy[a] * racc;
+    }
+    pos[(long long)row * F + f] = acc;
+  }
+}
+
+// x32[b,0,:] = pos[0,:]; x32[b,1+p,:] = tok[b,p,:] + pos[1+p,:]   (image_encoder_model.py:83-84)
+template <typename T>
+__global__ void assemble_tokens_kernel(const T* __restrict__ tok, const float* __restrict__ pos, float* __restrict__ x,
+                                       int B, int N, int F) {
+  const long long total = (long long)B * N * F / 4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx * 4;
+    const int f = (int)(e % F);
+    const long long row = e / F;
+    const int n = (int)(row % N);
+    const int b = (int)(row / N);
+    float4 pv = *reinterpret_cast<const float4*>(pos + (long long)n * F + f);
+    if (n > 0) {
+      const T* t = tok + ((long long)b * (N - 1) + (n - 1)) * F + f;
+      pv.x += to_f32(t[0]); pv.y += to_f32(t[1]); pv.z += to_f32(t[2]); pv.w += to_f32(t[3]);
+    }
+    *reinterpret_cast<float4*>(x + e) = pv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (biased variance), fp32 in -> 16-bit out. One warp per row, values held in registers.
+template <typename T, typename TIN>
+__global__ void layernorm_kernel(const TIN* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia,
+                                 T* __restrict__ y, long long M, int F, float eps) {
+  constexpr int MAXV = 12;  // F <= 1536
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const TIN* xr = x + row * F;
+  float4 v[MAXV];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int f = i * 128 + lane * 4;
+    if (f < F) {
+      if constexpr (sizeof(TIN) == 4) {
+        v[i] = *reinterpret_cast<const float4*>(xr + f);
+      } else {
+        v[i] = make_float4(to_f32(xr[f]), to_f32(xr[f + 1]), to_f32(xr[f + 2]), to_f32(xr[f + 3]));
+      }
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)F;
+  float var = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int f = i * 128 + lane * 4;
+    if (f < F) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      var += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / (float)F + eps);
+  T* yr = y + row * F;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int f = i * 128 + lane * 4;
+    if (f < F) {
+      const float4 ww = *reinterpret_cast<const float4*>(w + f);
+      const float4 bb = *reinterpret_cast<const float4*>(bia + f);
+      T o[4];
+      o[0] = from_f32<T>((v[i].x - mean) * rstd * ww.x + bb.x);
+      o[1] = from_f32<T>((v[i].y - mean) * rstd * ww.y + bb.y);
+      o[2] = from_f32<T>((v[i].z - mean) * rstd * ww.z + bb.z);
+      o[3] = from_f32<T>((v[i].w - mean) * rstd * ww.w + bb.w);
+      *reinterpret_cast<uint2*>(yr + f) = *reinterpret_cast<uint2*>(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bilinear resize, align_corners=True (misc_helpers.py:39-42), NHWC, 8 channels per thread.
+// src coordinate = dst * (in-1)/(out-1); matches ATen's area_pixel_compute_scale for align_corners.
+template <typename T>
+__global__ void resize_bilinear_ac_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int IH, int IW, int OH,
+                                          int OW, int C) {
+  const int cv = C / 8;
+  const long long total = (long long)B * OH * OW * cv;
+  const float sy = OH > 1 ? (float)(IH - 1) / (float)(OH - 1) : 0.0f;
+  const float sx = OW > 1 ? (float)(IW - 1) / (float)(OW - 1) : 0.0f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    long long t = idx / cv;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    const float fy = sy * oy, fx = sx * ox;
+    const int y0 = min((int)fy, IH - 1), x0 = min((int)fx, IW - 1);
+    const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const T* base = in + (long long)b * IH * IW * C + c8 * 8;
+    const Vec8<T> v00 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y0 * IW + x0) * C);
+    const Vec8<T> v01 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y0 * IW + x1) * C);
+    const Vec8<T> v10 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y1 * IW + x0) * C);
+    const Vec8<T> v11 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y1 * IW + x1) * C);
+    Vec8<T> o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r = hy * (hx * to_f32(v00.v[i]) + lx * to_f32(v01.v[i])) +
+                      ly * (hx * to_f32(v10.v[i]) + lx * to_f32(v11.v[i]));
+      o.v[i] = from_f32<T>(r);
+    }
+    *reinterpret_cast<Vec8<T>*>(out + (((long long)b * OH + oy) * OW + ox) * C + c8 * 8) = o;
+  }
+}
+
+// out = relu(in), 8 elements per thread
+template <typename T>
+__global__ void relu_copy_kernel(const T* __restrict__ in, T* __restrict__ out, long long n8) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    Vec8<T> v = reinterpret_cast<const Vec8<T>*>(in)[idx];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.v[i] = from_f32<T>(fmaxf(to_f32(v.v[i]), 0.0f));
+    reinterpret_cast<Vec8<T>*>(out)[idx] = v;
+  }
+}
+
+}  // namespace dpt

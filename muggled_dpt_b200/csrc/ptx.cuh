@@ -1,0 +1,180 @@
+// Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM).
+// Everything the GEMM / attention kernels need and nothing else. No CUTLASS dependency.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace dpt {
+
+#define DPT_DEVICE __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------------------------
+// misc
+
+DPT_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+DPT_DEVICE bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier
+
+DPT_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DPT_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DPT_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+DPT_DEVICE void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DPT_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DPT_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a broken pipeline traps (-> launch failure reported to the host) instead of hanging the GPU.
+DPT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at ~2 GHz
+      printf("dpt: mbarrier wait timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA
+
+DPT_DEVICE void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+DPT_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+DPT_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+DPT_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+         "r"(c3)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, MMA, commit, ld, fences
+
+DPT_DEVICE void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp; ncols power of 2 >= 32
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+DPT_DEVICE void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+DPT_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp (the allocating one)
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+DPT_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DPT_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues.
+DPT_DEVICE void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier once all previously issued MMAs of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+DPT_DEVICE void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// TMEM -> registers: thread t of the warp reads lane (32*(warp%4) + t), 32 consecutive 32-bit columns.
+DPT_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+DPT_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// descriptors
+
+// Shared-memory matrix descriptor for a tile whose rows are 128 bytes (64 x 16-bit) and that was written by TMA
+// with CU_TENSOR_MAP_SWIZZLE_128B into a 1024-byte-aligned buffer:
+//   K-major operand  : row r (an M or N index) at byte r*128, eight-row groups 1024 B apart (SBO = 1024).
+//   MN-major operand : row r (a K index) at byte r*128, the 64 contiguous elements are the M/N index (one swizzle
+//                      atom wide, so LBO is unused), eight-K-row groups 1024 B apart (SBO = 1024).
+// Field layout (PTX ISA "tcgen05 shared memory descriptor"): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
+// [46,48) version = 1, [61,64) swizzle mode (2 = 128B).
+DPT_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;             // LBO (ignored for 128B swizzle, canonical value 1)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO
+  d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for tcgen05.mma kind::f16, fp32 accumulate.
+//   [4,6) D format (1 = f32), [7,10) A format, [10,13) B format (0 = f16, 1 = bf16), [15] A major, [16] B major
+//   (0 = K-major, 1 = MN-major), [17,23) N>>3, [24,29) M>>4.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool is_bf16, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (is_bf16 ? 1u : 0u) << 7;
+  d |= (is_bf16 ? 1u : 0u) << 10;
+  d |= (a_mn_major ? 1u : 0u) << 15;
+  d |= (b_mn_major ? 1u : 0u) << 16;
+  d |= static_cast<uint32_t>(N >> 3) << 17;
+  d |= static_cast<uint32_t>(M >> 4) << 24;
+  return d;
+}
+
+}  // namespace dpt

@@ -1,0 +1,376 @@
+"""
+DPTModel - the reference's model wrapper surface (muggled_dpt/dpt_model.py:21-166) over libdpt_b200.so.
+
+Same calls as the reference: model(image_bchw), .inference(bgr), .prepare_image_bgr(...), .verify_input(...),
+.to(device=, dtype=, memory_format=), and the five stage attributes patch_embed / imgencoder / reassemble / fusion /
+head with the tensor signatures of simple_examples/internal_features.py:38-44. Everything below this surface runs in
+hand-written sm_100a kernels through the C ABI; PyTorch only owns the buffers. There is no CPU path: calling the model
+before `.to("cuda")`, or asking for fp32, raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .weights import pack_depthanything_v2
+
+_TORCH_TO_DPT = {torch.float16: N.DPT_F16, torch.bfloat16: N.DPT_BF16}
+
+
+class _Stage:
+    """callable stage wrapper (keeps `model.patch_embed(x)` etc. working)"""
+
+    def __init__(self, model: "DPTModel", fn):
+        self._model = model
+        self._fn = fn
+
+    def __call__(self, *args, **kwargs):
+        return self._fn(*args, **kwargs)
+
+
+class _PatchEmbedStage(_Stage):
+    # input normalisation constants - v2_depthanything/patch_embed.py:38-39
+    rgb_offset = (0.485, 0.456, 0.406)
+    rgb_stdev = (0.229, 0.224, 0.225)
+
+    def prepare_image(self, image_bgr, max_side_length=None, use_square_sizing=True, interpolation_mode="bilinear"):
+        """PatchEmbed.prepare_image - v2_depthanything/patch_embed.py:103-145 (host-side glue, outside forward())"""
+        m = self._model
+        patch = m.config["patch_size_px"]
+        default_size = m.config["base_patch_grid_hw"][0] * patch
+        tiling = round(2 * patch)
+        if max_side_length is None:
+            max_side_length = default_size
+        img_h, img_w = image_bgr.shape[0:2]
+        largest = max(img_h, img_w)
+        scale = max_side_length / largest
+        targ_hw = (largest, largest) if use_square_sizing else (img_h, img_w)
+        scaled_hw = [max(1, round(side * scale / tiling)) * tiling for side in targ_hw]
+        device, dtype = m._require_ready()
+        rgb = np.ascontiguousarray(image_bgr[:, :, ::-1])  # BGR -> RGB
+        chw = torch.tensor(np.transpose(rgb, (2, 0, 1)), device=device, dtype=dtype)
+        bchw = torch.nn.functional.interpolate(
+            chw.unsqueeze(0), size=scaled_hw, align_corners=False, antialias=True, mode=interpolation_mode
+        )
+        mean = torch.tensor(self.rgb_offset, device=device, dtype=dtype).view(-1, 1, 1)
+        inv_std = 1.0 / torch.tensor(self.rgb_stdev, device=device, dtype=dtype).view(-1, 1, 1)
+        return ((bchw / 255.0) - mean) * inv_std
+
+    def verify_input(self, image_tensor_bchw) -> bool:
+        """PatchEmbed.verify_input - v2_depthanything/patch_embed.py:149-165 (+ the even-grid rule the reference only
+        hits as a RuntimeError inside fusion)"""
+        b, c, h, w = image_tensor_bchw.shape
+        p = self._model.config["patch_size_px"]
+        assert c == 3, f"Bad channel count! Expected 3 got {c}"
+        assert h % p == 0, f"Bad height! Image must have height ({h}) divisble by {p}"
+        assert w % p == 0, f"Bad width! Image must have width ({w}) divisble by {p}"
+        assert (h // p) % 2 == 0 and (w // p) % 2 == 0, (
+            f"Bad size! The patch grid ({h // p}x{w // p}) must be even in both directions "
+            f"(use multiples of {2 * p} px, e.g. 504 or 532 instead of 518)"
+        )
+        return True
+
+
+class DPTModel(torch.nn.Module):
+    def __init__(self, config: dict, state_dict: dict, strict_load: bool = True):
+        super().__init__()
+        self.config = dict(config)
+        if self.config.get("is_giant", False):
+            raise NotImplementedError("ViT-G (SwiGLU) is not built in this round")
+        # fp32 CPU copies in kernel layouts; moved/cast by .to()
+        self._packed_cpu = pack_depthanything_v2(state_dict, self.config, strict=strict_load)
+        self._dev_weights: dict[str, torch.Tensor] = {}
+        self._handle = None
+        self._device = None
+        self._dtype = torch.bfloat16
+        self._workspace = None
+        self._ws_key = None
+        self._io = {}
+        self.patch_embed = _PatchEmbedStage(self, self._stage_patch_embed)
+        self.imgencoder = _Stage(self, self._stage_encoder)
+        self.reassemble = _Stage(self, self._stage_reassemble)
+        self.fusion = _Stage(self, self._stage_fusion)
+        self.head = _Stage(self, self._stage_head)
+        self.eval()
+
+    # ------------------------------------------------------------------------------------------------- placement
+
+    def to(self, *args, **kwargs):
+        device = kwargs.get("device", None)
+        dtype = kwargs.get("dtype", None)
+        for a in args:
+            if isinstance(a, torch.dtype):
+                dtype = a
+            elif isinstance(a, (str, torch.device, int)):
+                device = a
+        if dtype is not None:
+            if dtype not in _TORCH_TO_DPT:
+                raise RuntimeError(
+                    f"muggled_dpt_b200 computes in bf16 or fp16 (fp32 accumulate); {dtype} is only available from the "
+                    "reference / oracle CPU path"
+                )
+            self._dtype = dtype
+        if device is not None:
+            device = torch.device(device)
+            if device.type != "cuda":
+                raise RuntimeError("muggled_dpt_b200 has no CPU fallback: move the model to a B200 with .to('cuda')")
+            if device.index is None:
+                device = torch.device("cuda", torch.cuda.current_device())
+            self._device = device
+        if self._device is not None:
+            self._materialise()
+        return self
+
+    def cuda(self, device=None):
+        return self.to(device=torch.device("cuda", device) if isinstance(device, int) else (device or "cuda"))
+
+    def half(self):
+        return self.to(dtype=torch.float16)
+
+    def bfloat16(self):
+        return self.to(dtype=torch.bfloat16)
+
+    def float(self):
+        return self.to(dtype=torch.float32)
+
+    def parameters(self, recurse: bool = True):
+        # the reference's verify_input peeks at next(model.parameters()) for device / dtype
+        self._require_ready()
+        yield self._dev_weights["patch.w"]
+
+    def _require_ready(self):
+        if self._handle is None:
+            raise RuntimeError("model is not on a GPU yet: call .to('cuda') first (there is no CPU fallback)")
+        return self._device, self._dtype
+
+    def _materialise(self):
+        L = N.lib()
+        self._release()
+        with torch.cuda.device(self._device):
+            cfg = N.DptConfig()
+            cfg.variant = N.VARIANT_DINOV2
+            cfg.dtype = _TORCH_TO_DPT[self._dtype]
+            cfg.features_per_token = self.config["features_per_token"]
+            cfg.num_heads = self.config["num_heads"]
+            cfg.num_blocks = self.config["num_blocks"]
+            for i, r in enumerate(self.config["reassembly_features_list"]):
+                cfg.reassembly_features[i] = r
+            cfg.fusion_channels = self.config["fusion_channels"]
+            cfg.patch_size_px = self.config["patch_size_px"]
+            cfg.base_grid_h, cfg.base_grid_w = self.config["base_patch_grid_hw"]
+            cfg.is_metric = int(bool(self.config.get("is_metric", False)))
+            cfg.ln_eps = 1e-6
+            handle = C.c_void_p()
+            N.check(L.dpt_create(C.byref(cfg), C.byref(handle)), None, "dpt_create")
+            self._handle = handle
+            self._dev_weights = {}
+            for name, (t, kind) in self._packed_cpu.items():
+                if kind == "half":
+                    d, code = t.to(device=self._device, dtype=self._dtype), _TORCH_TO_DPT[self._dtype]
+                elif kind == "f32":
+                    d, code = t.to(device=self._device, dtype=torch.float32), N.DPT_F32
+                else:  # "host": tiny fp32 vectors the library copies into the handle
+                    d, code = t.to(dtype=torch.float32).contiguous(), N.DPT_F32
+                self._dev_weights[name] = d
+                shape = (C.c_int64 * max(1, d.dim()))(*d.shape)
+                N.check(
+                    L.dpt_set_weight(handle, name.encode(), C.c_void_p(d.data_ptr()), shape, d.dim(), code),
+                    handle, f"dpt_set_weight({name})",
+                )
+        self._workspace, self._ws_key, self._io = None, None, {}
+
+    def _release(self):
+        if self._handle is not None:
+            N.lib().dpt_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------- plumbing
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _get_workspace(self, B: int, H: int, W: int) -> torch.Tensor:
+        key = (B, H, W)
+        if self._ws_key != key:
+            need = C.c_size_t()
+            N.check(N.lib().dpt_workspace_bytes(self._handle, B, H, W, C.byref(need)), self._handle, "dpt_workspace_bytes")
+            self._workspace = None
+            self._workspace = torch.empty(int(need.value), dtype=torch.uint8, device=self._device)
+            self._ws_key = key
+        return self._workspace
+
+    def _check_image(self, x: torch.Tensor):
+        device, dtype = self._require_ready()
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected an image tensor of shape Bx3xHxW")
+        if x.device != device:
+            raise RuntimeError(f"Device mismatch! Image: {x.device}, model: {device}")
+        if x.dtype != dtype:
+            raise RuntimeError(f"Data type mismatch! Image: {x.dtype}, model: {dtype}")
+        p = self.config["patch_size_px"]
+        B, _, H, W = x.shape
+        if H % p or W % p or (H // p) % 2 or (W // p) % 2:
+            raise ValueError(
+                f"image size {H}x{W} is not usable: height and width must be multiples of {2 * p} "
+                "(even patch grid; the reference fails inside fusion otherwise)"
+            )
+        return B, H, W
+
+    # ------------------------------------------------------------------------------------------------- forward
+
+    def forward(self, image_rgb_normalized_bchw: torch.Tensor) -> torch.Tensor:
+        """DPTModel.forward (dpt_model.py:61-83): BxCxHxW -> BxHxW inverse depth, in the model dtype."""
+        B, H, W = self._check_image(image_rgb_normalized_bchw)
+        io = self._io.get((B, H, W))
+        if io is None:
+            io = (
+                torch.empty((B, 3, H, W), dtype=self._dtype, device=self._device),
+                torch.empty((B, H, W), dtype=self._dtype, device=self._device),
+            )
+            self._io = {(B, H, W): io}
+        img, out = io
+        img.copy_(image_rgb_normalized_bchw)  # fixed buffers keep the recorded launch plan valid across calls
+        self.forward_into(img, out)
+        return out.clone()
+
+    def forward_into(self, img: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """forward() on caller-owned, contiguous device buffers (no copies; used by bench.py)."""
+        B, H, W = self._check_image(img)
+        assert img.is_contiguous() and out.is_contiguous() and tuple(out.shape) == (B, H, W) and out.dtype == self._dtype
+        ws = self._get_workspace(B, H, W)
+        with torch.cuda.device(self._device):
+            rc = N.lib().dpt_forward(self._handle, C.c_void_p(img.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), B, H, W, self._stream())
+        N.check(rc, self._handle, "dpt_forward")
+        return out
+
+    def forward_host(self, host_img: torch.Tensor, host_out: torch.Tensor) -> torch.Tensor:
+        """Host buffers in/out through dpt_forward_host (H2D + forward + D2H + sync)."""
+        self._require_ready()
+        B, _, H, W = host_img.shape
+        io = self._io.get((B, H, W))
+        if io is None:
+            io = (
+                torch.empty((B, 3, H, W), dtype=self._dtype, device=self._device),
+                torch.empty((B, H, W), dtype=self._dtype, device=self._device),
+            )
+            self._io = {(B, H, W): io}
+        ws = self._get_workspace(B, H, W)
+        with torch.cuda.device(self._device):
+            rc = N.lib().dpt_forward_host(self._handle, C.c_void_p(host_img.data_ptr()), C.c_void_p(host_out.data_ptr()),
+                                          C.c_void_p(io[0].data_ptr()), C.c_void_p(io[1].data_ptr()),
+                                          C.c_void_p(ws.data_ptr()), ws.numel(), B, H, W, self._stream())
+        N.check(rc, self._handle, "dpt_forward_host")
+        return host_out
+
+    def last_launch_count(self) -> int:
+        return int(N.lib().dpt_last_launch_count(self._handle))
+
+    def inference(self, image_bgr, max_side_length=None, use_square_sizing=True) -> torch.Tensor:
+        """DPTModel.inference (dpt_model.py:87-109)"""
+        with torch.inference_mode():
+            x = self.patch_embed.prepare_image(image_bgr, max_side_length, use_square_sizing)
+            return self(x)
+
+    def prepare_image_bgr(self, image_bgr, max_side_length=None, use_square_sizing=True, interpolation_mode="bilinear"):
+        """DPTModel.prepare_image_bgr (dpt_model.py:113-129)"""
+        return self.patch_embed.prepare_image(image_bgr, max_side_length, use_square_sizing, interpolation_mode)
+
+    def verify_input(self, image_rgb_normalized_bchw) -> bool:
+        """DPTModel.verify_input (dpt_model.py:133-166): AssertionError on bad input, True otherwise"""
+        assert isinstance(image_rgb_normalized_bchw, torch.Tensor), "Image must be provided as a tensor!"
+        device, dtype = self._require_ready()
+        x = image_rgb_normalized_bchw
+        assert x.device == device, f"Device mismatch! Image: {x.device}, model: {device}"
+        assert x.dtype == dtype, f"Data type mismatch! Image: {x.dtype}, model: {dtype}"
+        shape_str = "x".join(str(s) for s in x.shape)
+        assert x.dim() == 4, f"Bad image shape! Image ({shape_str}) should have a shape of BxCXHxW"
+        return self.patch_embed.verify_input(x)
+
+    # ------------------------------------------------------------------------------------------------- stages
+
+    def _grid(self, H, W):
+        p = self.config["patch_size_px"]
+        return H // p, W // p
+
+    def _stage_ws(self, B, gh, gw):
+        p = self.config["patch_size_px"]
+        return self._get_workspace(B, gh * p, gw * p)
+
+    def _stage_patch_embed(self, image_bchw: torch.Tensor):
+        B, H, W = self._check_image(image_bchw)
+        gh, gw = self._grid(H, W)
+        F = self.config["features_per_token"]
+        img = image_bchw.contiguous()
+        tokens = torch.empty((B, gh * gw, F), dtype=self._dtype, device=self._device)
+        ws = self._get_workspace(B, H, W)
+        rc = N.lib().dpt_patch_embed(self._handle, C.c_void_p(img.data_ptr()), C.c_void_p(tokens.data_ptr()),
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), B, H, W, self._stream())
+        N.check(rc, self._handle, "dpt_patch_embed")
+        return tokens, (gh, gw)
+
+    def _stage_encoder(self, patch_tokens: torch.Tensor, patch_grid_hw):
+        gh, gw = int(patch_grid_hw[0]), int(patch_grid_hw[1])
+        B, Np, F = patch_tokens.shape
+        assert Np == gh * gw and patch_tokens.dtype == self._dtype
+        tok = patch_tokens.contiguous()
+        taps = [torch.empty((B, Np + 1, F), dtype=self._dtype, device=self._device) for _ in range(4)]
+        ws = self._stage_ws(B, gh, gw)
+        rc = N.lib().dpt_encoder(self._handle, C.c_void_p(tok.data_ptr()), C.byref(N.ptr4(taps)),
+                                 C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        N.check(rc, self._handle, "dpt_encoder")
+        return tuple(taps)
+
+    def _nhwc_empty(self, B, Cc, H, W):
+        # logical [B,C,H,W] with channels_last strides == the kernels' [B,H,W,C]
+        return torch.empty((B, H, W, Cc), dtype=self._dtype, device=self._device).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def _as_nhwc(t: torch.Tensor) -> torch.Tensor:
+        return t.contiguous(memory_format=torch.channels_last)
+
+    def _stage_reassemble(self, s1, s2, s3, s4, patch_grid_hw):
+        gh, gw = int(patch_grid_hw[0]), int(patch_grid_hw[1])
+        B = s1.shape[0]
+        Cc = self.config["fusion_channels"]
+        taps = [t.contiguous() for t in (s1, s2, s3, s4)]
+        sizes = [(gh * 4, gw * 4), (gh * 2, gw * 2), (gh, gw), (gh // 2, gw // 2)]
+        maps = [self._nhwc_empty(B, Cc, h, w) for h, w in sizes]
+        ws = self._stage_ws(B, gh, gw)
+        rc = N.lib().dpt_reassemble(self._handle, C.byref(N.ptr4(taps)), C.byref(N.ptr4(maps)),
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        N.check(rc, self._handle, "dpt_reassemble")
+        return tuple(maps)
+
+    def _stage_fusion(self, r1, r2, r3, r4):
+        maps = [self._as_nhwc(t) for t in (r1, r2, r3, r4)]
+        B, Cc, h3, w3 = maps[2].shape
+        gh, gw = h3, w3
+        fused = self._nhwc_empty(B, Cc, gh * 8, gw * 8)
+        ws = self._stage_ws(B, gh, gw)
+        rc = N.lib().dpt_fusion(self._handle, C.byref(N.ptr4(maps)), C.c_void_p(fused.data_ptr()),
+                                C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        N.check(rc, self._handle, "dpt_fusion")
+        return fused
+
+    def _stage_head(self, fused: torch.Tensor):
+        x = self._as_nhwc(fused)
+        B, Cc, h, w = x.shape
+        gh, gw = h // 8, w // 8
+        p = self.config["patch_size_px"]
+        depth = torch.empty((B, gh * p, gw * p), dtype=self._dtype, device=self._device)
+        ws = self._stage_ws(B, gh, gw)
+        rc = N.lib().dpt_head(self._handle, C.c_void_p(x.data_ptr()), C.c_void_p(depth.data_ptr()),
+                              C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        N.check(rc, self._handle, "dpt_head")
+        return depth

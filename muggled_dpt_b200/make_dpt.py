@@ -1,0 +1,63 @@
+"""
+make_dpt_from_state_dict - same signature and return value as the reference factory
+(muggled_dpt/make_dpt.py:21-72): loads an upstream checkpoint, sniffs the model type, infers the config from the
+tensor shapes and returns (config_dict, model). The model it returns is the B200-native DPTModel; move it to the GPU
+with `model.to(device="cuda", dtype=torch.bfloat16)` exactly like the reference demos do (run_image.py:158).
+"""
+
+from __future__ import annotations
+
+from time import sleep
+
+import torch
+
+from .dpt_model import DPTModel
+from .weights import determine_model_type_from_state_dict, get_model_config_from_state_dict
+
+
+def make_dpt_from_state_dict(
+    path_to_state_dict: str,
+    enable_cache: bool = False,
+    enable_optimizations: bool = True,
+    strict_load: bool = True,
+    model_type: str | None = None,
+) -> tuple[dict, DPTModel]:
+    # weights are packed on the host first, so always load to CPU (reference: cuda load with cpu fallback, :38-41)
+    state_dict = torch.load(path_to_state_dict, map_location="cpu")
+
+    if model_type is None:
+        model_type = determine_model_type_from_state_dict(path_to_state_dict, state_dict)
+
+    known_model_types = ["swinv2", "beit", "depthanythingv1", "depthanythingv2"]
+    if model_type not in known_model_types:
+        print("Accepted model types:", *known_model_types, sep="\n")
+        raise NotImplementedError(f"Bad model type: {model_type}, no support for this yet!")
+    if model_type != "depthanythingv2":
+        raise NotImplementedError(
+            f"Model type {model_type} is recognised but its B200 encoder is not built yet (SURVEY.md section 8: configs W/E, 8f)"
+        )
+
+    # metric models are indistinguishable by weights; the reference keys off the file name (make_dpt.py:56-66)
+    if model_type == "depthanythingv2" and "metric" in path_to_state_dict:
+        state_dict["is_metric"] = torch.tensor((1), dtype=torch.float32)
+        print("", "Warning: Metric Depth-Anything V2 model detected!", "  These models are not officially supported,",
+              "  model outputs may be incorrect...", sep="\n", flush=True)
+        sleep(1.5)
+
+    return make_depthanythingv2_dpt_from_original_state_dict(state_dict, enable_cache, enable_optimizations, strict_load)
+
+
+def make_depthanythingv2_dpt_from_original_state_dict(
+    state_dict: dict,
+    enable_cache: bool = False,
+    enable_optimizations: bool = True,
+    strict_load: bool = True,
+) -> tuple[dict, DPTModel]:
+    """make_depthanythingv2_dpt.py:24-61. enable_cache / enable_optimizations are accepted for signature parity: the
+    position table is always precomputed per grid and the fused attention kernel is the only attention path."""
+    if not strict_load:
+        print("", "WARNING:", "  Loading model weights without 'strict' mode enabled!",
+              "  Some weights may be missing or unused!", sep="\n", flush=True)
+    config_dict = get_model_config_from_state_dict(state_dict, enable_cache, enable_optimizations)
+    model = DPTModel(config_dict, state_dict, strict_load=strict_load)
+    return config_dict, model

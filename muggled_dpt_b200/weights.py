@@ -1,0 +1,220 @@
+"""
+Weight loader for the B200 depth path: upstream checkpoint -> (config dict, packed device tensors).
+
+Behaviour mirrors the reference loader for Depth-Anything V2
+(muggled_dpt/v2_depthanything/state_dict_conversion/config_from_original_state_dict.py:17-43 and
+ convert_original_state_dict_keys.py:15-86,295-317): the model hyper-parameters are inferred from tensor shapes, the
+position embedding is split into cls / patch parts, `pretrained.mask_token` and
+`depth_head.scratch.refinenet4.resConfUnit1.*` are silently dropped. Instead of renaming keys into five nn.Module
+state dicts, the tensors are packed straight into the layouts the sm_100a kernels consume:
+
+  * every matmul weight is [N, taps * kpad] K-major 16-bit with kpad = roundup(Cin, 64) (zero padded), tap = ky*3+kx
+    for 3x3 kernels (gemm_tc.cuh); ConvTranspose2d(k=s) becomes s*s stacked [Cout, kpad] matrices, one per (ky, kx);
+  * LayerScale is folded into the preceding Linear: gamma*(Wx+b) = (gamma*W)x + gamma*b (transformer_block.py:58,63);
+  * biases, LayerNorm parameters and the position embedding stay fp32.
+"""
+
+from __future__ import annotations
+
+import math
+import re
+
+import torch
+
+GEMM_K = 64
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# model-type sniffing (muggled_dpt/make_dpt.py:78-116)
+
+
+def determine_model_type_from_state_dict(model_path: str, state_dict: dict) -> str:
+    import os.path as osp
+
+    keys = state_dict.keys()
+    if "pretrained.model.layers.0.blocks.0.attn.logit_scale" in keys:
+        return "swinv2"
+    if "pretrained.model.blocks.0.attn.relative_position_bias_table" in keys:
+        return "beit"
+    if "pretrained.blocks.0.ls1.gamma" in keys:
+        name = osp.basename(model_path).lower()
+        is_v2 = "v2" in name
+        is_v1 = (not is_v2) and (("anything_vit" in name) or ("v1" in name))
+        if (not is_v1) and (not is_v2):
+            print("", "WARNING: Unable to determine DepthAnything model version!", "-> Will assume v2",
+                  "-> Will use v1 if the file name contains 'v1'", sep="\n")
+        return "depthanythingv1" if is_v1 else "depthanythingv2"
+    return "unknown"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config inference - same keys, same order as the reference's config dict
+
+
+def get_model_config_from_state_dict(state_dict: dict, enable_cache: bool, enable_optimizations: bool) -> dict:
+    def need(key):
+        assert key in state_dict, f"Error determining model config! Couldn't find {key} key"
+        return state_dict[key]
+
+    pe = need("pretrained.patch_embed.proj.weight")
+    features_per_token = int(pe.shape[0])
+    patch_size_px = int(pe.shape[3])
+    block_ids = [int(m.group(1)) for m in (re.match(r"pretrained\.blocks\.(\d+)\.", k) for k in state_dict) if m]
+    assert block_ids and max(block_ids) > 0, "Error determining number of transformer blocks! Could not find any blocks"
+    reasm = [int(need(f"depth_head.scratch.layer{i}_rn.weight").shape[1]) for i in (1, 2, 3, 4)]
+    num_tokens = int(need("pretrained.pos_embed").shape[1]) - 1
+    base = int(math.isqrt(num_tokens))
+    return {
+        "features_per_token": features_per_token,
+        "num_blocks": 1 + max(block_ids),
+        "num_heads": features_per_token // 64,
+        "reassembly_features_list": reasm,
+        "fusion_channels": int(need("depth_head.scratch.layer1_rn.weight").shape[0]),
+        "patch_size_px": patch_size_px,
+        "base_patch_grid_hw": (base, base),
+        "is_giant": "pretrained.blocks.0.mlp.w12.weight" in state_dict,
+        "is_metric": "is_metric" in state_dict,
+        "enable_cache": enable_cache,
+        "enable_optimizations": enable_optimizations,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# packing helpers (pure tensor reshapes - unit-tested on CPU in tests/test_weights.py)
+
+
+def _roundup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] -> [N, roundup(K, 64)] zero padded"""
+    n, k = w.shape
+    out = w.new_zeros(n, _roundup(k, GEMM_K))
+    out[:, :k] = w
+    return out
+
+
+def pack_conv(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [Cout, Cin, kh, kw] -> [Cout, kh*kw*kpad], column = (ky*kw + kx)*kpad + ci"""
+    co, ci, kh, kw = w.shape
+    kpad = _roundup(ci, GEMM_K)
+    out = w.new_zeros(co, kh * kw, kpad)
+    out[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+    return out.reshape(co, kh * kw * kpad)
+
+
+def pack_conv_transpose(w: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d(k = stride = s) weight [Cin, Cout, s, s] -> [s*s*Cout, kpad]; block (ky*s + kx) holds
+    W_sub[co, ci] = w[ci, co, ky, kx], so out[b, y*s+ky, x*s+kx, co] = sum_ci in[b,y,x,ci] * W_sub[co, ci] + bias[co]
+    (reassembly_model.py:262-269)."""
+    ci, co, s, s2 = w.shape
+    assert s == s2
+    kpad = _roundup(ci, GEMM_K)
+    out = w.new_zeros(s * s, co, kpad)
+    out[:, :, :ci] = w.permute(2, 3, 1, 0).reshape(s * s, co, ci)
+    return out.reshape(s * s * co, kpad)
+
+
+def pack_patch_embed(w: torch.Tensor) -> torch.Tensor:
+    """[F, 3, P, P] -> [F, roundup(3*P*P, 64)], column = c*P*P + ky*P + kx (patch_embed.py:92-97)"""
+    return pack_linear(w.reshape(w.shape[0], -1))
+
+
+def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
+    """Returns {packed name: (fp32 cpu tensor, kind)} with kind in {"half", "f32", "host"}."""
+    F = cfg["features_per_token"]
+    L = cfg["num_blocks"]
+    missing = []
+
+    def get(key, default_shape=None, fill=0.0):
+        if key in sd:
+            return sd[key].detach().to(torch.float32).cpu()
+        missing.append(key)
+        if strict or default_shape is None:
+            return None
+        return torch.full(default_shape, fill)
+
+    out = {}
+
+    def put(name, t, kind):
+        if t is not None:
+            out[name] = (t.contiguous(), kind)
+
+    pw = get("pretrained.patch_embed.proj.weight")
+    put("patch.w", pack_patch_embed(pw) if pw is not None else None, "half")
+    put("patch.b", get("pretrained.patch_embed.proj.bias", (F,)), "f32")
+    pos = get("pretrained.pos_embed")
+    if pos is not None:
+        put("pos.cls_emb", pos[0, 0, :].clone(), "f32")
+        put("pos.base", pos[0, 1:, :].clone(), "f32")
+    cls = get("pretrained.cls_token", (1, 1, F))
+    put("pos.cls_tok", cls.reshape(-1) if cls is not None else None, "f32")
+    for i in range(L):
+        s, d = f"pretrained.blocks.{i}.", f"blk{i}."
+        put(d + "ln1.w", get(s + "norm1.weight", (F,), 1.0), "f32")
+        put(d + "ln1.b", get(s + "norm1.bias", (F,)), "f32")
+        put(d + "ln2.w", get(s + "norm2.weight", (F,), 1.0), "f32")
+        put(d + "ln2.b", get(s + "norm2.bias", (F,)), "f32")
+        qw = get(s + "attn.qkv.weight", (3 * F, F))
+        put(d + "qkv.w", pack_linear(qw) if qw is not None else None, "half")
+        put(d + "qkv.b", get(s + "attn.qkv.bias", (3 * F,)), "f32")
+        g1 = get(s + "ls1.gamma", (F,), 1.0)
+        g2 = get(s + "ls2.gamma", (F,), 1.0)
+        w, b = get(s + "attn.proj.weight", (F, F)), get(s + "attn.proj.bias", (F,))
+        if all(t is not None for t in (g1, w, b)):
+            put(d + "proj.w", pack_linear(g1[:, None] * w), "half")
+            put(d + "proj.b", g1 * b, "f32")
+        w1 = get(s + "mlp.fc1.weight", (4 * F, F))
+        put(d + "fc1.w", pack_linear(w1) if w1 is not None else None, "half")
+        put(d + "fc1.b", get(s + "mlp.fc1.bias", (4 * F,)), "f32")
+        w, b = get(s + "mlp.fc2.weight", (F, 4 * F)), get(s + "mlp.fc2.bias", (F,))
+        if all(t is not None for t in (g2, w, b)):
+            put(d + "fc2.w", pack_linear(g2[:, None] * w), "half")
+            put(d + "fc2.b", g2 * b, "f32")
+    put("outnorm.w", get("pretrained.norm.weight", (F,), 1.0), "f32")
+    put("outnorm.b", get("pretrained.norm.bias", (F,)), "f32")
+
+    for k in range(4):
+        d = f"reasm{k}."
+        w = get(f"depth_head.projects.{k}.weight")
+        put(d + "proj.w", pack_linear(w.reshape(w.shape[0], -1)) if w is not None else None, "half")
+        put(d + "proj.b", get(f"depth_head.projects.{k}.bias"), "f32")
+        if k in (0, 1):
+            w = get(f"depth_head.resize_layers.{k}.weight")
+            put(d + "up.w", pack_conv_transpose(w) if w is not None else None, "half")
+            put(d + "up.b", get(f"depth_head.resize_layers.{k}.bias"), "f32")
+        elif k == 3:
+            w = get("depth_head.resize_layers.3.weight")
+            put(d + "down.w", pack_conv(w) if w is not None else None, "half")
+            put(d + "down.b", get("depth_head.resize_layers.3.bias"), "f32")
+        w = get(f"depth_head.scratch.layer{k + 1}_rn.weight")
+        put(d + "fuse.w", pack_conv(w) if w is not None else None, "half")
+
+    for lvl in range(4):
+        s, d = f"depth_head.scratch.refinenet{lvl + 1}.", f"fus{lvl}."
+        units = (("rcu1", "resConfUnit1"), ("rcu2", "resConfUnit2")) if lvl < 3 else (("rcu2", "resConfUnit2"),)
+        for dn, sn in units:  # refinenet4.resConfUnit1 is dropped (convert_original_state_dict_keys.py:230)
+            for cv in (1, 2):
+                w = get(f"{s}{sn}.conv{cv}.weight")
+                put(f"{d}{dn}.c{cv}.w", pack_conv(w) if w is not None else None, "half")
+                put(f"{d}{dn}.c{cv}.b", get(f"{s}{sn}.conv{cv}.bias"), "f32")
+        w = get(s + "out_conv.weight")
+        put(d + "out.w", pack_linear(w.reshape(w.shape[0], -1)) if w is not None else None, "half")
+        put(d + "out.b", get(s + "out_conv.bias"), "f32")
+
+    s = "depth_head.scratch."
+    w = get(s + "output_conv1.weight")
+    put("head.c1.w", pack_conv(w) if w is not None else None, "half")
+    put("head.c1.b", get(s + "output_conv1.bias"), "f32")
+    w = get(s + "output_conv2.0.weight")
+    put("head.c2.w", pack_conv(w) if w is not None else None, "half")
+    put("head.c2.b", get(s + "output_conv2.0.bias"), "f32")
+    w = get(s + "output_conv2.2.weight")
+    put("head.c3.w_host", w.reshape(-1) if w is not None else None, "host")
+    put("head.c3.b_host", get(s + "output_conv2.2.bias"), "host")
+
+    if missing and strict:
+        raise RuntimeError("Error(s) in loading state_dict: Missing key(s): " + ", ".join(missing[:8]) +
+                           (" ..." if len(missing) > 8 else ""))
+    return out

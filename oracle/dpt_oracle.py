@@ -1,0 +1,272 @@
+"""
+ORACLE - TEST INFRASTRUCTURE ONLY. Nothing under muggled_dpt_b200/ may import this module; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs do, and only as the checker / the timed
+CPU baseline - never as the product path.
+
+A flat, functional, fp32, CPU restatement of the reference's single-image depth inference path
+(muggled_dpt/dpt_model.py:61-83) for Depth-Anything V2 (DINOv2 ViT-S/B/L + DPT head), written directly against the
+UPSTREAM checkpoint key names (the format make_dpt_from_state_dict() loads), so it shares no code and no key-renaming
+logic with either the reference or the product. The arithmetic itself lives in PyTorch (third-party; the reference
+pins torch>=2.1,<2.10, this image has 2.11): every op below is the same ATen call the reference module makes, cited
+file:line. Parity pinning: the reference ships no tests / golden vectors, so this oracle is pinned
+against the reference itself, imported in the build container from /root/reference by oracle/make_golden.py, on seeded
+synthetic checkpoints; the resulting fixtures are committed under tests/golden/ and checked by
+tests/test_oracle_golden.py (stage by stage).
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config inference (v2_depthanything/state_dict_conversion/config_from_original_state_dict.py:17-43)
+
+
+def infer_config(sd: dict) -> dict:
+    feats = int(sd["pretrained.patch_embed.proj.weight"].shape[0])
+    patch = int(sd["pretrained.patch_embed.proj.weight"].shape[3])
+    blocks = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("pretrained.blocks."))
+    ntok = int(sd["pretrained.pos_embed"].shape[1]) - 1
+    base = int(math.isqrt(ntok))
+    reasm = [int(sd[f"depth_head.scratch.layer{i}_rn.weight"].shape[1]) for i in (1, 2, 3, 4)]
+    return {
+        "features_per_token": feats,
+        "num_blocks": blocks,
+        "num_heads": feats // 64,  # :78-90
+        "reassembly_features_list": reasm,
+        "fusion_channels": int(sd["depth_head.scratch.layer1_rn.weight"].shape[0]),
+        "patch_size_px": patch,
+        "base_patch_grid_hw": (base, base),
+        "is_metric": "is_metric" in sd,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stages
+
+
+def patch_embed(sd: dict, img_bchw: torch.Tensor):
+    """PatchEmbed.forward - v2_depthanything/patch_embed.py:77-99"""
+    w, b = sd["pretrained.patch_embed.proj.weight"], sd["pretrained.patch_embed.proj.bias"]
+    p = w.shape[-1]
+    x = F.conv2d(img_bchw, w, b, stride=p)
+    grid_hw = tuple(x.shape[2:])
+    return x.flatten(2).transpose(1, 2), grid_hw
+
+
+def position_table(sd: dict, grid_hw) -> tuple[torch.Tensor, torch.Tensor]:
+    """PositionEncoder - components/position_encoder.py:55-76,108-143 (bicubic, align_corners=False, fp32)"""
+    pos = sd["pretrained.pos_embed"].float()
+    cls_pos, patch_pos = pos[:, :1], pos[:, 1:]
+    n, c = patch_pos.shape[1:]
+    base = int(math.isqrt(n))
+    img = patch_pos.reshape(1, base, base, c).permute(0, 3, 1, 2)
+    img = F.interpolate(img, size=tuple(grid_hw), mode="bicubic", antialias=False)
+    return cls_pos, img.permute(0, 2, 3, 1).reshape(1, -1, c)
+
+
+def layernorm(x, w, b, eps=1e-6):
+    """LayerNormEPS6 - components/misc_helpers.py:190-210"""
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def attention(sd: dict, pre: str, x: torch.Tensor, heads: int, use_sdpa: bool = True):
+    """OptimizedAttention.forward / Attention.forward - components/transformer_block.py:154-170 / 105-136"""
+    B, N, C = x.shape
+    d = C // heads
+    qkv = F.linear(x, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"])
+    qkv = qkv.reshape(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.unbind(0)
+    if use_sdpa:
+        o = F.scaled_dot_product_attention(q, k, v)
+    else:
+        a = (q * d**-0.5) @ k.transpose(-2, -1)
+        o = a.softmax(dim=-1) @ v
+    o = o.transpose(1, 2).reshape(B, N, C)
+    return F.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+
+
+def mlp(sd: dict, pre: str, x: torch.Tensor):
+    """MLP2Layers.forward - components/misc_helpers.py:88-120 (exact-erf GELU)"""
+    h = F.gelu(F.linear(x, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))
+    return F.linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+
+
+def block(sd: dict, i: int, x: torch.Tensor, heads: int, use_sdpa: bool = True):
+    """TransformerBlock.forward - components/transformer_block.py:53-65"""
+    pre = f"pretrained.blocks.{i}."
+    a = attention(sd, pre, layernorm(x, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"]), heads, use_sdpa)
+    x = x + sd[pre + "ls1.gamma"] * a
+    m = mlp(sd, pre, layernorm(x, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"]))
+    return x + sd[pre + "ls2.gamma"] * m
+
+
+def encoder(sd: dict, cfg: dict, tokens: torch.Tensor, grid_hw, use_sdpa: bool = True):
+    """DinoV2Model4Stages.forward - v2_depthanything/image_encoder_model.py:80-94 (taps after uniform stages)"""
+    cls_pos, patch_pos = position_table(sd, grid_hw)
+    cls = (sd["pretrained.cls_token"] + cls_pos).to(tokens.dtype)
+    x = torch.cat((cls.expand(tokens.shape[0], -1, -1), tokens + patch_pos.to(tokens.dtype)), dim=1)
+    per_stage = int(round(cfg["num_blocks"] / 4))
+    taps = []
+    for i in range(cfg["num_blocks"]):
+        x = block(sd, i, x, cfg["num_heads"], use_sdpa)
+        if (i + 1) % per_stage == 0:
+            taps.append(x)
+    nw, nb = sd["pretrained.norm.weight"], sd["pretrained.norm.bias"]
+    return tuple(layernorm(t, nw, nb) for t in taps[:4])
+
+
+def reassemble(sd: dict, taps, grid_hw):
+    """ReassembleModel.forward - v2_depthanything/reassembly_model.py:61-94,139-149"""
+    outs = []
+    for k, t in enumerate(taps):
+        x = t[:, 1:, :].transpose(1, 2).unflatten(2, tuple(grid_hw))  # :142, :208-211
+        x = F.conv2d(x, sd[f"depth_head.projects.{k}.weight"], sd[f"depth_head.projects.{k}.bias"])
+        if k in (0, 1):  # ConvTranspose2d k = s = 4 / 2 (:262-269)
+            s = 4 if k == 0 else 2
+            x = F.conv_transpose2d(
+                x, sd[f"depth_head.resize_layers.{k}.weight"], sd[f"depth_head.resize_layers.{k}.bias"], stride=s
+            )
+        elif k == 3:  # Conv2d k=3 s=2 p=1 (:302-309)
+            x = F.conv2d(
+                x, sd["depth_head.resize_layers.3.weight"], sd["depth_head.resize_layers.3.bias"], stride=2, padding=1
+            )
+        x = F.conv2d(x, sd[f"depth_head.scratch.layer{k + 1}_rn.weight"], None, padding=1)  # fuse_proj, no bias
+        outs.append(x)
+    return tuple(outs)
+
+
+def _rcu(sd: dict, pre: str, x: torch.Tensor):
+    """ResidualConv2D.forward - v2_depthanything/fusion_model.py:187-220"""
+    y = F.conv2d(F.relu(x), sd[pre + "conv1.weight"], sd[pre + "conv1.bias"], padding=1)
+    y = F.conv2d(F.relu(y), sd[pre + "conv2.weight"], sd[pre + "conv2.bias"], padding=1)
+    return y + x
+
+
+def _upsample_project(sd: dict, rn: str, x: torch.Tensor):
+    """UpsampleProjectionBlock - fusion_model.py:159-182"""
+    x = _rcu(sd, rn + "resConfUnit2.", x)
+    x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    return F.conv2d(x, sd[rn + "out_conv.weight"], sd[rn + "out_conv.bias"])
+
+
+def fusion(sd: dict, r1, r2, r3, r4):
+    """FusionModel.forward - v2_depthanything/fusion_model.py:55-80 (refinenet4.resConfUnit1 unused)"""
+    pre = "depth_head.scratch.refinenet"
+    f = _upsample_project(sd, pre + "4.", r4)
+    for idx, r in ((3, r3), (2, r2), (1, r1)):
+        rn = f"{pre}{idx}."
+        f = _upsample_project(sd, rn, _rcu(sd, rn + "resConfUnit1.", r) + f)
+    return f
+
+
+def head(sd: dict, cfg: dict, x: torch.Tensor):
+    """MonocularDepthHead.forward - v2_depthanything/head_model.py:61-106"""
+    p = "depth_head.scratch."
+    x = F.conv2d(x, sd[p + "output_conv1.weight"], sd[p + "output_conv1.bias"], padding=1)
+    x = F.interpolate(x, scale_factor=cfg["patch_size_px"] / 8, mode="bilinear", align_corners=True)
+    x = F.relu(F.conv2d(x, sd[p + "output_conv2.0.weight"], sd[p + "output_conv2.0.bias"], padding=1))
+    x = F.conv2d(x, sd[p + "output_conv2.2.weight"], sd[p + "output_conv2.2.bias"])
+    x = torch.sigmoid(x) if cfg.get("is_metric", False) else F.relu(x)
+    return x.squeeze(1)
+
+
+def forward(sd: dict, img_bchw: torch.Tensor, cfg: dict | None = None, return_stages: bool = False, use_sdpa=True):
+    """DPTModel.forward - muggled_dpt/dpt_model.py:61-83"""
+    cfg = cfg or infer_config(sd)
+    with torch.inference_mode():
+        tokens, grid_hw = patch_embed(sd, img_bchw)
+        taps = encoder(sd, cfg, tokens, grid_hw, use_sdpa)
+        maps = reassemble(sd, taps, grid_hw)
+        fused = fusion(sd, *maps)
+        depth = head(sd, cfg, fused)
+    if return_stages:
+        return {"tokens": tokens, "taps": taps, "maps": maps, "fused": fused, "depth": depth, "grid_hw": grid_hw}
+    return depth
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic upstream-format checkpoints (key schema + weight distributions that give O(1) stages)
+
+STANDARD_CONFIGS = {
+    # make_depthanythingv2_dpt.py:88-122
+    "vits": dict(F=384, blocks=12, reasm=(48, 96, 192, 384), C=64),
+    "vitb": dict(F=768, blocks=12, reasm=(96, 192, 384, 768), C=128),
+    "vitl": dict(F=1024, blocks=24, reasm=(256, 512, 1024, 1024), C=256),
+    # not a real model: small enough to commit its weights-free fixtures and run anywhere in milliseconds
+    "tiny": dict(F=128, blocks=4, reasm=(16, 32, 64, 128), C=32),
+}
+
+
+def make_synthetic_state_dict(name: str = "vits", seed: int = 0, base_grid: int = 37, patch: int = 14) -> dict:
+    cfg = STANDARD_CONFIGS[name]
+    Fdim, L, R, C = cfg["F"], cfg["blocks"], cfg["reasm"], cfg["C"]
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    def fan(*shape):  # fan-in scaled normal
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        return rn(*shape, std=fan_in**-0.5)
+
+    sd = {}
+    sd["pretrained.cls_token"] = rn(1, 1, Fdim, std=0.5)
+    sd["pretrained.pos_embed"] = rn(1, 1 + base_grid * base_grid, Fdim, std=0.5)
+    sd["pretrained.mask_token"] = rn(1, Fdim)
+    sd["pretrained.patch_embed.proj.weight"] = fan(Fdim, 3, patch, patch)
+    sd["pretrained.patch_embed.proj.bias"] = rn(Fdim, std=0.1)
+    for i in range(L):
+        p = f"pretrained.blocks.{i}."
+        for nrm in ("norm1", "norm2"):
+            sd[p + nrm + ".weight"] = 1.0 + rn(Fdim, std=0.1)
+            sd[p + nrm + ".bias"] = rn(Fdim, std=0.1)
+        sd[p + "attn.qkv.weight"] = fan(3 * Fdim, Fdim) * 1.5
+        sd[p + "attn.qkv.bias"] = rn(3 * Fdim, std=0.1)
+        sd[p + "attn.proj.weight"] = fan(Fdim, Fdim)
+        sd[p + "attn.proj.bias"] = rn(Fdim, std=0.1)
+        sd[p + "ls1.gamma"] = 0.05 + 0.95 * torch.rand(Fdim, generator=g)
+        sd[p + "ls2.gamma"] = 0.05 + 0.95 * torch.rand(Fdim, generator=g)
+        sd[p + "mlp.fc1.weight"] = fan(4 * Fdim, Fdim)
+        sd[p + "mlp.fc1.bias"] = rn(4 * Fdim, std=0.1)
+        sd[p + "mlp.fc2.weight"] = fan(Fdim, 4 * Fdim)
+        sd[p + "mlp.fc2.bias"] = rn(Fdim, std=0.1)
+    sd["pretrained.norm.weight"] = 1.0 + rn(Fdim, std=0.1)
+    sd["pretrained.norm.bias"] = rn(Fdim, std=0.1)
+    for k in range(4):
+        sd[f"depth_head.projects.{k}.weight"] = fan(R[k], Fdim, 1, 1)
+        sd[f"depth_head.projects.{k}.bias"] = rn(R[k], std=0.1)
+    sd["depth_head.resize_layers.0.weight"] = rn(R[0], R[0], 4, 4, std=R[0] ** -0.5)
+    sd["depth_head.resize_layers.0.bias"] = rn(R[0], std=0.1)
+    sd["depth_head.resize_layers.1.weight"] = rn(R[1], R[1], 2, 2, std=R[1] ** -0.5)
+    sd["depth_head.resize_layers.1.bias"] = rn(R[1], std=0.1)
+    sd["depth_head.resize_layers.3.weight"] = fan(R[3], R[3], 3, 3)
+    sd["depth_head.resize_layers.3.bias"] = rn(R[3], std=0.1)
+    for k in range(4):
+        sd[f"depth_head.scratch.layer{k + 1}_rn.weight"] = fan(C, R[k], 3, 3)
+    for i in (1, 2, 3, 4):
+        for u in (1, 2):
+            for cv in (1, 2):
+                p = f"depth_head.scratch.refinenet{i}.resConfUnit{u}.conv{cv}."
+                sd[p + "weight"] = fan(C, C, 3, 3) * (1.4 if cv == 1 else 0.7)
+                sd[p + "bias"] = rn(C, std=0.1)
+        sd[f"depth_head.scratch.refinenet{i}.out_conv.weight"] = fan(C, C, 1, 1)
+        sd[f"depth_head.scratch.refinenet{i}.out_conv.bias"] = rn(C, std=0.1)
+    sd["depth_head.scratch.output_conv1.weight"] = fan(C // 2, C, 3, 3)
+    sd["depth_head.scratch.output_conv1.bias"] = rn(C // 2, std=0.1)
+    sd["depth_head.scratch.output_conv2.0.weight"] = fan(32, C // 2, 3, 3) * 1.4
+    sd["depth_head.scratch.output_conv2.0.bias"] = rn(32, std=0.1) + 0.2
+    sd["depth_head.scratch.output_conv2.2.weight"] = fan(1, 32, 1, 1)
+    sd["depth_head.scratch.output_conv2.2.bias"] = torch.full((1,), 2.0)
+    return sd
+
+
+def make_input(B: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
+    g = torch.Generator().manual_seed(1000 + seed)
+    return torch.randn(B, 3, H, W, generator=g)

@@ -1,0 +1,61 @@
+"""helpers for the -m gpu tests: call the C ABI operators on torch CUDA tensors"""
+import ctypes as C
+
+import torch
+
+from muggled_dpt_b200 import _native as N
+
+DT = {torch.float16: N.DPT_F16, torch.bfloat16: N.DPT_BF16}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def conv_gemm(A, Wt, bias=None, add1=None, add2=None, want_relu=False, taps=1, xoff=0, act=0, out_f32=False, N_out=None):
+    """A [B,H,W,C] 16-bit, Wt [N, taps*kpad] 16-bit -> out [B,H,W-xoff,N]"""
+    B, H, W, Cc = A.shape
+    n = N_out if N_out is not None else Wt.shape[0]
+    out = torch.empty((B, H, W - xoff, n), device=A.device, dtype=torch.float32 if out_f32 else A.dtype)
+    out_relu = torch.empty_like(out) if want_relu else None
+    rc = N.lib().dpt_op_conv_gemm(_p(A), _p(Wt), _p(bias), _p(out), _p(add1), _p(add2), _p(out_relu), B, H, W, Cc, n,
+                                  taps, xoff, act, int(out_f32), DT[A.dtype], _stream())
+    N.check(rc, None, "dpt_op_conv_gemm")
+    torch.cuda.synchronize()
+    return (out, out_relu) if want_relu else out
+
+
+def attention(qkv, heads, scale, bias=None):
+    B, n, F3 = qkv.shape
+    out = torch.empty((B, n, F3 // 3), device=qkv.device, dtype=qkv.dtype)
+    rc = N.lib().dpt_op_attention(_p(qkv), _p(bias), _p(out), B, n, heads, float(scale), DT[qkv.dtype], _stream())
+    N.check(rc, None, "dpt_op_attention")
+    torch.cuda.synchronize()
+    return out
+
+
+def layernorm(x, w, b, eps, dtype):
+    M, F = x.shape
+    y = torch.empty((M, F), device=x.device, dtype=dtype)
+    rc = N.lib().dpt_op_layernorm(_p(x), _p(w), _p(b), _p(y), M, F, float(eps), DT[dtype], _stream())
+    N.check(rc, None, "dpt_op_layernorm")
+    torch.cuda.synchronize()
+    return y
+
+
+def resize(x, OH, OW):
+    B, IH, IW, Cc = x.shape
+    y = torch.empty((B, OH, OW, Cc), device=x.device, dtype=x.dtype)
+    rc = N.lib().dpt_op_resize_bilinear(_p(x), _p(y), B, IH, IW, OH, OW, Cc, DT[x.dtype], _stream())
+    N.check(rc, None, "dpt_op_resize_bilinear")
+    torch.cuda.synchronize()
+    return y
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item(), (a - b).abs().max().item()

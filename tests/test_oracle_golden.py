@@ -1,0 +1,68 @@
+"""CPU: the oracle restatement (oracle/dpt_oracle.py) against the golden vectors produced by the real reference
+(oracle/make_golden.py, run in the build container). The reference ships no tests of its own, so
+these fixtures are what pins the oracle."""
+import os
+
+import pytest
+import torch
+
+from oracle import dpt_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fixture(name):
+    fix = torch.load(os.path.join(GOLDEN, name))
+    sd = fix.get("state_dict") or O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"])
+    return fix, sd
+
+
+@pytest.mark.parametrize("name", ["tiny_a.pt", "tiny_b.pt"])
+def test_oracle_matches_reference_every_stage(name):
+    fix, sd = _fixture(name)
+    st = O.forward(sd, fix["img"], return_stages=True)
+    assert tuple(st["grid_hw"]) == tuple(fix["grid_hw"])
+    torch.testing.assert_close(st["tokens"], fix["tokens"], rtol=0, atol=1e-6)
+    for a, b in zip(st["taps"], fix["taps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=2e-5)
+    for a, b in zip(st["maps"], fix["maps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=5e-5)
+    torch.testing.assert_close(st["fused"], fix["fused"], rtol=0, atol=1e-4)
+    torch.testing.assert_close(st["depth"], fix["depth"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["vits_a.pt", "vits_b.pt"])
+def test_oracle_matches_reference_vits(name):
+    from oracle.make_golden import state_dict_checksum, sub
+
+    fix, sd = _fixture(name)
+    assert state_dict_checksum(sd) == fix["sd_checksum"]
+    st = O.forward(sd, fix["img"], return_stages=True)
+    torch.testing.assert_close(sub(st["tokens"]), fix["tokens_sub"], rtol=0, atol=1e-5)
+    for a, b in zip(st["taps"], fix["taps_sub"]):
+        torch.testing.assert_close(sub(a), b, rtol=0, atol=1e-4)
+    for a, b in zip(st["maps"], fix["maps_sub"]):
+        torch.testing.assert_close(sub(a), b, rtol=0, atol=2e-4)
+    torch.testing.assert_close(st["depth"], fix["depth"], rtol=0, atol=5e-4)
+
+
+def test_oracle_manual_attention_equals_sdpa():
+    fix, sd = _fixture("tiny_a.pt")
+    a = O.forward(sd, fix["img"], use_sdpa=True)
+    b = O.forward(sd, fix["img"], use_sdpa=False)
+    torch.testing.assert_close(a, b, rtol=0, atol=5e-5)
+
+
+def test_oracle_config_inference():
+    sd = O.make_synthetic_state_dict("vits", seed=11)
+    cfg = O.infer_config(sd)
+    assert cfg["features_per_token"] == 384 and cfg["num_blocks"] == 12 and cfg["num_heads"] == 6
+    assert cfg["reassembly_features_list"] == [48, 96, 192, 384] and cfg["fusion_channels"] == 64
+    assert cfg["base_patch_grid_hw"] == (37, 37) and cfg["patch_size_px"] == 14
+
+
+def test_oracle_rejects_odd_grid_like_the_reference():
+    # 518 / 14 = 37 (odd): the reference raises inside fusion; so does the restatement
+    sd = O.make_synthetic_state_dict("tiny", seed=3, base_grid=5)
+    with pytest.raises(RuntimeError):
+        O.forward(sd, O.make_input(1, 42, 42))

@@ -1,0 +1,128 @@
+"""CPU: weight loader / packer. Every packed layout is checked by evaluating the GEMM formulation the kernels use
+(gemm_tc.cuh) in torch and comparing with the reference op (F.conv2d / F.conv_transpose2d / F.linear)."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from muggled_dpt_b200 import weights as Wt
+from oracle import dpt_oracle as O
+
+
+def _im2col3x3(x_nhwc, kpad):
+    B, H, W, C = x_nhwc.shape
+    xp = F.pad(x_nhwc, (0, kpad - C, 1, 1, 1, 1))
+    cols = [xp[:, ky:ky + H, kx:kx + W, :] for ky in range(3) for kx in range(3)]
+    return torch.cat(cols, dim=-1)  # [B,H,W,9*kpad], column = tap*kpad + c
+
+
+def test_pack_conv_matches_conv2d():
+    torch.manual_seed(0)
+    x = torch.randn(2, 7, 9, 24)
+    w = torch.randn(40, 24, 3, 3)
+    packed = Wt.pack_conv(w)
+    assert packed.shape == (40, 9 * 64)
+    got = _im2col3x3(x, 64) @ packed.t()
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("s", [2, 4])
+def test_pack_conv_transpose_matches_conv_transpose2d(s):
+    torch.manual_seed(1)
+    ci = co = 24
+    x = torch.randn(2, 5, 6, ci)
+    w = torch.randn(ci, co, s, s)
+    b = torch.randn(co)
+    packed = Wt.pack_conv_transpose(w)
+    assert packed.shape == (s * s * co, 64)
+    xp = F.pad(x, (0, 64 - ci))
+    out = torch.zeros(2, 5 * s, 6 * s, co)
+    for sub in range(s * s):
+        ky, kx = sub // s, sub % s
+        out[:, ky::s, kx::s, :] = xp @ packed[sub * co:(sub + 1) * co].t() + b
+    ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), w, b, stride=s).permute(0, 2, 3, 1)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_pack_patch_embed_matches_strided_conv():
+    torch.manual_seed(2)
+    P, Fd = 14, 32
+    img = torch.randn(2, 3, 28, 42)
+    w = torch.randn(Fd, 3, P, P)
+    packed = Wt.pack_patch_embed(w)
+    assert packed.shape == (Fd, 640)
+    gh, gw = 2, 3
+    cols = img.reshape(2, 3, gh, P, gw, P).permute(0, 2, 4, 1, 3, 5).reshape(2, gh * gw, 3 * P * P)
+    got = F.pad(cols, (0, 640 - 588)) @ packed.t()
+    ref = F.conv2d(img, w, stride=P).flatten(2).transpose(1, 2)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_layerscale_folding():
+    torch.manual_seed(3)
+    sd = O.make_synthetic_state_dict("tiny", seed=3, base_grid=5)
+    cfg = Wt.get_model_config_from_state_dict(sd, False, True)
+    packed = Wt.pack_depthanything_v2(sd, cfg)
+    x = torch.randn(5, 128)
+    ref = sd["pretrained.blocks.1.ls1.gamma"] * F.linear(x, sd["pretrained.blocks.1.attn.proj.weight"],
+                                                         sd["pretrained.blocks.1.attn.proj.bias"])
+    got = x @ packed["blk1.proj.w"][0].t() + packed["blk1.proj.b"][0]
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_config_matches_reference_keys_and_values():
+    sd = O.make_synthetic_state_dict("vits", seed=11)
+    cfg = Wt.get_model_config_from_state_dict(sd, enable_cache=False, enable_optimizations=True)
+    # key set and order of the reference's config dict (config_from_original_state_dict.py:29-41)
+    assert list(cfg.keys()) == ["features_per_token", "num_blocks", "num_heads", "reassembly_features_list",
+                                "fusion_channels", "patch_size_px", "base_patch_grid_hw", "is_giant", "is_metric",
+                                "enable_cache", "enable_optimizations"]
+    ocfg = O.infer_config(sd)
+    for k, v in ocfg.items():
+        assert cfg[k] == v, k
+
+
+def test_dropped_and_missing_keys():
+    sd = O.make_synthetic_state_dict("tiny", seed=3, base_grid=5)
+    cfg = Wt.get_model_config_from_state_dict(sd, False, True)
+    packed = Wt.pack_depthanything_v2(sd, cfg)
+    assert not any(k.startswith("fus3.rcu1") for k in packed)  # refinenet4.resConfUnit1 is dropped
+    sd2 = dict(sd)
+    del sd2["pretrained.blocks.2.mlp.fc2.bias"]
+    with pytest.raises(RuntimeError):
+        Wt.pack_depthanything_v2(sd2, cfg, strict=True)
+    Wt.pack_depthanything_v2(sd2, cfg, strict=False)
+
+
+def test_model_type_sniffing():
+    f = Wt.determine_model_type_from_state_dict
+    assert f("x.pth", {"pretrained.model.layers.0.blocks.0.attn.logit_scale": 0}) == "swinv2"
+    assert f("x.pth", {"pretrained.model.blocks.0.attn.relative_position_bias_table": 0}) == "beit"
+    assert f("depth_anything_v2_vits.pth", {"pretrained.blocks.0.ls1.gamma": 0}) == "depthanythingv2"
+    assert f("depth_anything_vitl14.pth", {"pretrained.blocks.0.ls1.gamma": 0}) == "depthanythingv1"
+    assert f("x.pth", {}) == "unknown"
+
+
+def test_factory_surface_on_cpu():
+    from muggled_dpt_b200 import make_dpt_from_state_dict
+
+    sd = O.make_synthetic_state_dict("tiny", seed=3, base_grid=5)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "depth_anything_v2_tiny.pth")
+        torch.save(sd, path)
+        cfg, model = make_dpt_from_state_dict(path)
+        with pytest.raises(NotImplementedError):
+            make_dpt_from_state_dict(path, model_type="nonsense")
+    assert cfg["num_blocks"] == 4
+    for attr in ("patch_embed", "imgencoder", "reassemble", "fusion", "head", "inference", "prepare_image_bgr",
+                 "verify_input", "to"):
+        assert hasattr(model, attr)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        model(torch.zeros(1, 3, 56, 56))
+    with pytest.raises(RuntimeError):
+        model.to("cpu")
+    with pytest.raises(RuntimeError):
+        model.to(dtype=torch.float32)
