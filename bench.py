@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""
+bench.py - depth frames/s of the DPT hot path (DPTModel.forward) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--model vitl|vitb|vits]
+                  [--batch B] [--size S] [--dtype bf16|fp16] [--scaling strong|weak]
+
+Workload (BASELINE.json metric "depth frames/sec at 518^2 ViT-L bf16, 1/2/4/8xB200", configs[2]): Depth-Anything-V2
+ViT-L, global batch 32, 504x504 (the reference's effective "518" setting - SURVEY.md section 0.1: 518 has an odd patch grid
+and the reference's forward raises), bf16, synthetic seeded weights and inputs. One "step" = one forward of the
+global batch. N>1: the batch is sharded over ranks (strong scaling, per-rank batch 32/N), every rank runs the same
+kernels on its frames and the depth maps are all-gathered once per step over NCCL.
+
+Printed JSON line (rank 0): value = frames/s with inputs resident in HBM (CUDA events, max over ranks);
+e2e = same metric through the host-buffer C-ABI call (dpt_forward_host: pinned host -> H2D -> forward -> D2H);
+roofline = the dominant kernel (tcgen05 GEMM) from per-launch CUDA events recorded inside the library during extra
+profiled steps; cpu_baseline = the oracle's fp32 CPU restatement of the reference path on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "depth_frames_per_sec"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="vitl", choices=["vitl", "vitb", "vits", "tiny"])
+    ap.add_argument("--batch", type=int, default=32, help="global batch (frames per step)")
+    ap.add_argument("--size", type=int, default=504)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--cpu-baseline-frames", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--dump-profile", default="", help="write the per-launch table to this path")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return {"tflops_sustained": pk.get("bf16_tflops_sustained", 1413.6), "tflops_burst": pk.get("bf16_tflops", 1685.6),
+                "hbm_gbs": pk.get("hbm_gbs", 6538.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def algorithmic_gflop_per_frame(model, size):
+    """BASELINE.md section 3 (torch flop counter on the reference modules, 2*MAC, matmul/conv only)."""
+    table = {("vits", 504): 107.32, ("vitb", 504): 356.69, ("vitl", 504): 1224.94, ("vitl", 532): 1385.8}
+    return table.get((model, size))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def time_cpu_oracle(model_name, size, frames, threads=None):
+    """fp32 CPU restatement of the reference path (oracle/), B=1 per step: returns (frames/s, cores, sample text)"""
+    import torch
+
+    from oracle import dpt_oracle as O
+
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    sd = O.make_synthetic_state_dict(model_name, seed=11)
+    img = O.make_input(1, size, size, seed=2)
+    O.forward(sd, img)  # warm-up
+    ts = []
+    for _ in range(frames):
+        t0 = time.perf_counter()
+        O.forward(sd, img)
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    sample = f"{frames} frames of B=1 {model_name} {size}x{size} fp32 after 1 warm-up, median; torch threads={cores} of {os.cpu_count()} cpus"
+    return 1.0 / med, cores, sample
+
+
+def run_reference(args, rank, world):
+    """reference arm: the reference's own CPU implementation of the path == the oracle port (the reference is pure
+    Python/PyTorch and /root/reference does not exist on the GPU box), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import dpt_oracle as O
+
+    cores = torch.get_num_threads()
+    sd = O.make_synthetic_state_dict(args.model, seed=11)
+    img = O.make_input(1, args.size, args.size, seed=2)
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.forward(sd, img)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.forward(sd, img)
+    dt = time.perf_counter() - t0
+    fps = steps / dt
+    sample = (f"each step = 1 frame (a bounded sample of the batch-{args.batch} workload) of {args.model} "
+              f"{args.size}x{args.size}, fp32 CPU, {steps} timed steps; torch threads={cores} of {os.cpu_count()} cpus")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Depth-Anything-V2 {args.model} {args.size}x{args.size}, global batch {args.batch} "
+                               "(reference's effective 518 setting)", "parallelism": "host cpu"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from muggled_dpt_b200 import make_dpt_from_state_dict
+    from oracle import dpt_oracle as O  # synthetic checkpoint generator + cpu_baseline only
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    if args.scaling == "strong":
+        assert args.batch % world == 0, "global batch must divide over ranks"
+        b_local = args.batch // world
+        b_global = args.batch
+    else:
+        b_local = args.batch
+        b_global = args.batch * world
+    S = args.size
+
+    # ---- model (synthetic seeded checkpoint in the upstream format, loaded through the reference-shaped factory)
+    sd = O.make_synthetic_state_dict(args.model, seed=11)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, f"depth_anything_v2_{args.model}_synthetic.pth")
+        torch.save(sd, path)
+        del sd
+        cfg, model = make_dpt_from_state_dict(path)
+    model.to(device=dev, dtype=dtype, memory_format=torch.channels_last)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_img = torch.randn(b_local, 3, S, S, generator=g).to(dtype).pin_memory()
+    host_out = torch.empty(b_local, S, S, dtype=dtype).pin_memory()
+    img = host_img.to(dev)
+    out = torch.empty(b_local, S, S, dtype=dtype, device=dev)
+    gathered = torch.empty(b_global, S, S, dtype=dtype, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        flush.zero_()  # L2 flush between iterations (B200_PROFILING.md timing hygiene)
+        model.forward_into(img, out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    with torch.inference_mode():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ms_total = timed(step, args.steps)
+        clocks = sampler.stop() if rank == 0 else None
+        launches_per_step = model.last_launch_count() + 1 + (1 if world > 1 else 0)
+        ms_per_step = ms_total / args.steps
+        fps = b_global * args.steps / (ms_total / 1000.0)
+
+        # ---- e2e: host buffers through the C ABI (H2D + forward + D2H inside the timed region, every step)
+        e2e = None
+        if not args.no_e2e:
+            def step_host():
+                model.forward_host(host_img, host_out)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, model._io[(b_local, S, S)][1])
+            for _ in range(2):
+                step_host()
+            ms_e2e = timed(step_host, args.steps)
+            e2e = {"value": b_global * args.steps / (ms_e2e / 1000.0), "unit": UNIT,
+                   "h2d_bytes_per_step": host_img.numel() * host_img.element_size() * world,
+                   "d2h_bytes_per_step": host_out.numel() * host_out.element_size() * world,
+                   "ms_per_step": ms_e2e / args.steps,
+                   "path": "DPTModel.forward_host -> dpt_forward_host (pinned host buffers)"}
+
+        # ---- roofline leg: per-launch CUDA events inside the library on extra steps
+        roofline, breakdown = None, None
+        if rank == 0 and args.profile_steps > 0:
+            model.enable_profiling(True)
+            agg = {}
+            for _ in range(args.profile_steps):
+                flush.zero_()
+                model.forward_into(img, out)
+                torch.cuda.synchronize()
+                for label, ms, fl, by in model.read_profile():
+                    fam = label.split(":")[0]
+                    a = agg.setdefault(fam, [0.0, 0.0, 0.0, 0])
+                    a[0] += ms; a[1] += fl; a[2] += by; a[3] += 1
+                last_profile = model.read_profile()
+            model.enable_profiling(False)
+            tot_ms = sum(a[0] for a in agg.values())
+            breakdown = {fam: {"ms_per_step": a[0] / args.profile_steps, "share": a[0] / tot_ms,
+                               "tflops": (a[1] / (a[0] / 1000.0) / 1e12) if a[0] > 0 else 0.0,
+                               "gbs": (a[2] / (a[0] / 1000.0) / 1e9) if a[0] > 0 else 0.0,
+                               "launches_per_step": a[3] // args.profile_steps} for fam, a in agg.items()}
+            peaks = load_peaks()
+            dom = max(agg.items(), key=lambda kv: kv[1][0])[0]
+            a = agg[dom]
+            if a[1] > 0:
+                ach = a[1] / (a[0] / 1000.0) / 1e12
+                roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"],
+                            "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                            "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+                            "avg_launch_ms": a[0] / a[3], "flop_per_launch": a[1] / a[3],
+                            "share_of_step": a[0] / tot_ms}
+            else:
+                ach = a[2] / (a[0] / 1000.0) / 1e9
+                roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                            "avg_launch_ms": a[0] / a[3], "share_of_step": a[0] / tot_ms}
+            if args.dump_profile:
+                with open(args.dump_profile, "w") as f:
+                    f.write("label,ms,gflop,mbytes,tflops,gbs\n")
+                    for label, ms, fl, by in last_profile:
+                        f.write(f"{label},{ms:.4f},{fl / 1e9:.3f},{by / 1e6:.3f},"
+                                f"{(fl / (ms / 1e3) / 1e12) if ms > 0 else 0:.1f},{(by / (ms / 1e3) / 1e9) if ms > 0 else 0:.0f}\n")
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on this box's host cores
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = time_cpu_oracle(args.model, S, args.cpu_baseline_frames)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        gf = algorithmic_gflop_per_frame(args.model, S)
+        peaks = load_peaks()
+        line = {
+            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"Depth-Anything-V2 {args.model} (synthetic seeded weights), global batch {b_global}, "
+                            f"3x{S}x{S} (reference's effective 518 setting), {args.dtype}",
+                "global_batch": b_global, "per_gpu_batch": b_local, "parallelism": f"dp{world} batch-shard + all-gather",
+                "l2": "256 MiB buffer rewritten between iterations (L2 flush); per-step working set >> 126 MB L2",
+            },
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "kernel_breakdown": breakdown,
+        }
+        if gf:
+            tf = gf * 1e9 * fps / 1e12
+            line["model_tflops"] = {"algorithmic_gflop_per_frame": gf, "achieved_tflops_whole_job": tf,
+                                    "frac_of_sustained_peak_per_gpu": tf / world / peaks["tflops_sustained"]}
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,13 @@ int dpt_op_resize_bilinear(const void* in, void* out, int B, int IH, int IW, int
                            void* stream);
 const char* dpt_op_last_error(void);
 
+/* Per-launch CUDA-event timing of the launches of the most recent dpt_forward / stage call (bench.py's roofline
+ * leg). Enable, run, synchronize the stream, then read entry i: label ("gemm256:blk3.fc1", "attn:blk3.", ...),
+ * elapsed ms, algorithmic FLOPs (2*MAC, unpadded) and algorithmic HBM bytes of that launch. */
+int dpt_profile_enable(dpt_handle h, int on);
+int dpt_profile_count(dpt_handle h);
+int dpt_profile_get(dpt_handle h, int i, char* label, int label_len, double* ms, double* flops, double* bytes);
+
 /* number of kernels the most recent dpt_forward / stage call launched (bench.py's gpu_launches) */
 int dpt_last_launch_count(dpt_handle h);
 

@@ -63,6 +63,9 @@ SYMBOLS = [
     ("dpt_op_resize_bilinear", _I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     ("dpt_op_last_error", C.c_char_p, []),
     ("dpt_last_launch_count", _I, [_VP]),
+    ("dpt_profile_enable", _I, [_VP, _I]),
+    ("dpt_profile_count", _I, [_VP]),
+    ("dpt_profile_get", _I, [_VP, _I, C.c_char_p, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 
 

@@ -34,7 +34,14 @@ struct Weight {
   int dtype = 0;
 };
 
-using LaunchFn = std::function<cudaError_t(cudaStream_t)>;
+using LaunchFnRaw = std::function<cudaError_t(cudaStream_t)>;
+struct LaunchFn {
+  LaunchFnRaw fn;
+  std::string label;   // kernel family + layer, e.g. "gemm256:blk3.fc1"
+  double flops = 0;    // algorithmic FLOPs (2*MAC, unpadded)
+  double bytes = 0;    // algorithmic HBM bytes (operands read once + outputs written once)
+  cudaError_t operator()(cudaStream_t s) const { return fn(s); }
+};
 
 struct Plan {
   std::vector<LaunchFn> launches;
@@ -74,6 +81,11 @@ struct dpt_model_s {
   int last_launches = 0;
   int num_sms = 148;
   int device = 0;
+  // optional per-launch CUDA-event timing (bench.py's roofline leg)
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<std::string> prof_labels;
+  std::vector<double> prof_flops, prof_bytes;
 };
 
 namespace {
@@ -87,10 +99,19 @@ struct Ctx {
   bool ok = true;
   int is_bf16;
   int num_sms;
+  std::string scope;  // label prefix for launches recorded by the current stage builder
   bool fail(const std::string& s) {
     if (ok) err = s;
     ok = false;
     return false;
+  }
+  void add(const std::string& label, double flops, double bytes, LaunchFnRaw fn) {
+    LaunchFn l;
+    l.fn = std::move(fn);
+    l.label = label;
+    l.flops = flops;
+    l.bytes = bytes;
+    launches->push_back(std::move(l));
   }
 };
 
@@ -183,6 +204,7 @@ struct GemmOp {
   const float* head_w = nullptr;      // host pointer to 32 floats (OUT_HEAD)
   float head_b = 0.f;
   int head_act = ACT_RELU;
+  const char* label = "";
 };
 
 bool add_gemm(Ctx& c, GemmOp op) {
@@ -248,7 +270,18 @@ bool add_gemm(Ctx& c, GemmOp op) {
 
   const long long total = (long long)p.B * p.tiles_y * p.tiles_x * p.n_tiles;
   const int grid = (int)std::min<long long>(total, c.num_sms);
-  c.launches->push_back([p, bn, grid](cudaStream_t s) { return launch_gemm(p, bn, grid, s); });
+  {
+    const double pix = (double)op.B * op.H * op.W;
+    const double flops = 2.0 * pix * op.N * op.C * op.taps;
+    const double osz = op.out_kind == OUT_F32 ? 4.0 : 2.0;
+    double bytes = pix * op.C * 2.0 + (double)op.N * op.taps * op.kpad * 2.0 +
+                   (op.out_kind == OUT_HEAD ? pix * 2.0 : pix * op.N * osz);
+    if (op.add1) bytes += pix * op.N * osz;
+    if (op.add2) bytes += pix * op.N * 2.0;
+    if (op.out2_relu) bytes += pix * op.N * 2.0;
+    c.add("gemm" + std::to_string(bn) + ":" + c.scope + op.label, flops, bytes,
+          [p, bn, grid](cudaStream_t s) { return launch_gemm(p, bn, grid, s); });
+  }
   return true;
 }
 
@@ -268,7 +301,8 @@ bool add_attention(Ctx& c, const void* qkv, const void* bias, void* out, int B, 
   p.bias = bias;
   p.ldb = N;
   dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
-  c.launches->push_back([p, grid](cudaStream_t s) {
+  c.add("attn:" + c.scope, 4.0 * B * heads * (double)N * N * 64.0, 4.0 * (double)B * N * F * 2.0,
+        [p, grid](cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
@@ -297,7 +331,7 @@ bool add_layernorm(Ctx& c, const float* x, const float* w, const float* b, void*
   if (F % 4 != 0 || F > 1536) return c.fail("layernorm: F must be a multiple of 4 and <= 1536");
   if (c.dry) return true;
   const int is_bf16 = c.is_bf16;
-  c.launches->push_back([=](cudaStream_t s) {
+  c.add("layernorm:" + c.scope, 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
     const int rows_per_block = 8;
     const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
     DISPATCH_T(is_bf16, (layernorm_kernel<T, float><<<grid, rows_per_block * 32, 0, s>>>(x, w, b, (T*)y, M, F, eps)));
@@ -311,7 +345,7 @@ bool add_resize(Ctx& c, const void* in, void* out, int B, int IH, int IW, int OH
   if (c.dry) return true;
   const int is_bf16 = c.is_bf16;
   const int nsm = c.num_sms;
-  c.launches->push_back([=](cudaStream_t s) {
+  c.add("resize:" + c.scope, 0.0, ((double)B * IH * IW + (double)B * OH * OW) * C * 2.0, [=](cudaStream_t s) {
     const long long total = (long long)B * OH * OW * (C / 8);
     const int grid = ew_grid(total, 256, nsm);
     DISPATCH_T(is_bf16, (resize_bilinear_ac_kernel<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, B, IH, IW, OH, OW, C)));
@@ -325,7 +359,7 @@ bool add_relu_copy(Ctx& c, const void* in, void* out, long long n) {
   if (c.dry) return true;
   const int is_bf16 = c.is_bf16;
   const int nsm = c.num_sms;
-  c.launches->push_back([=](cudaStream_t s) {
+  c.add("relu_copy:" + c.scope, 0.0, (double)n * 4.0, [=](cudaStream_t s) {
     const int grid = ew_grid(n / 8, 256, nsm);
     DISPATCH_T(is_bf16, (relu_copy_kernel<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, n / 8)));
     return cudaGetLastError();
@@ -368,7 +402,7 @@ bool build_patch_embed(Ctx& c, const void* img, void* tokens, int B, int H, int 
   void* A = c.ar.alloc((size_t)M * kpad * 2);
   if (!c.dry) {
     const int is_bf16 = c.is_bf16, nsm = c.num_sms;
-    c.launches->push_back([=](cudaStream_t s) {
+    c.add("im2col_patch", 0.0, (double)B * 3 * H * W * 2.0 + (double)M * kpad * 2.0, [=](cudaStream_t s) {
       const int grid = ew_grid(M * kpad, 256, nsm);
       DISPATCH_T(is_bf16, (im2col_patch_kernel<T><<<grid, 256, 0, s>>>((const T*)img, (T*)A, B, 3, H, W, P, gh, gw, kpad)));
       return cudaGetLastError();
@@ -379,6 +413,8 @@ bool build_patch_embed(Ctx& c, const void* img, void* tokens, int B, int H, int 
   op.Wt_ptr = w->ptr; op.N = F; op.taps = 1; op.kpad = kpad;
   op.bias = (const float*)b->ptr;
   op.out = tokens;
+  op.label = "patch_embed";
+  c.scope = "";
   bool ok = add_gemm(c, op);
   c.ar.reset(mk);
   return ok;
@@ -412,11 +448,11 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     const int bh = cfg.base_grid_h, bw = cfg.base_grid_w;
     const int is_bf16 = c.is_bf16, nsm = c.num_sms;
     const float *bp = (const float*)base->ptr, *ct = (const float*)cls_tok->ptr, *ce = (const float*)cls_emb->ptr;
-    c.launches->push_back([=](cudaStream_t s) {
+    c.add("pos_table", 0.0, (double)N * F * 4.0, [=](cudaStream_t s) {
       pos_table_kernel<<<N, 128, 0, s>>>(bp, ct, ce, pos, bh, bw, gh, gw, F);
       return cudaGetLastError();
     });
-    c.launches->push_back([=](cudaStream_t s) {
+    c.add("assemble_tokens", 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
       const int grid = ew_grid(M * F / 4, 256, nsm);
       DISPATCH_T(is_bf16, (assemble_tokens_kernel<T><<<grid, 256, 0, s>>>((const T*)tokens, pos, x, B, N, F)));
       return cudaGetLastError();
@@ -433,35 +469,37 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     const Weight *f2w = get_w(c, pre + "fc2.w", hd), *f2b = get_w(c, pre + "fc2.b", DPT_F32);
     if (!c.ok) return false;
     const int hidden = (int)f1w->shape[0];
+    c.scope = pre;
     add_layernorm(c, x, (const float*)l1w->ptr, (const float*)l1b->ptr, ln, M, F, cfg.ln_eps);
     {
       GemmOp op;
       op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = qw->ptr; op.N = 3 * F; op.kpad = (int)qw->shape[1];
-      op.bias = (const float*)qb->ptr; op.out = qkv;
+      op.bias = (const float*)qb->ptr; op.out = qkv; op.label = "qkv";
       add_gemm(c, op);
     }
     add_attention(c, qkv, nullptr, att, B, N, heads, scale);
     {
       GemmOp op;  // x += (gamma1 . proj)(att)   (LayerScale folded into the packed weights)
       op.A = att; op.Wt = (int)M; op.C = F; op.Wt_ptr = pw->ptr; op.N = F; op.kpad = (int)pw->shape[1];
-      op.bias = (const float*)pb->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x;
+      op.bias = (const float*)pb->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x; op.label = "proj";
       add_gemm(c, op);
     }
     add_layernorm(c, x, (const float*)l2w->ptr, (const float*)l2b->ptr, ln, M, F, cfg.ln_eps);
     {
       GemmOp op;
       op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = hidden; op.kpad = (int)f1w->shape[1];
-      op.bias = (const float*)f1b->ptr; op.act = ACT_GELU; op.out = hid;
+      op.bias = (const float*)f1b->ptr; op.act = ACT_GELU; op.out = hid; op.label = "fc1";
       add_gemm(c, op);
     }
     {
       GemmOp op;
       op.A = hid; op.Wt = (int)M; op.C = hidden; op.Wt_ptr = f2w->ptr; op.N = F; op.kpad = (int)f2w->shape[1];
-      op.bias = (const float*)f2b->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x;
+      op.bias = (const float*)f2b->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x; op.label = "fc2";
       add_gemm(c, op);
     }
     if ((i + 1) % per_stage == 0) {
       const int st = (i + 1) / per_stage - 1;
+      c.scope = "outnorm" + std::to_string(st);
       add_layernorm(c, x, (const float*)on_w->ptr, (const float*)on_b->ptr, taps[st], M, F, cfg.ln_eps);
     }
   }
@@ -486,13 +524,14 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
     const Weight* fw = get_w(c, pre + "fuse.w", hd);
     if (!c.ok) return false;
     const size_t mk2 = c.ar.mark();
+    c.scope = pre;
     // 1x1 projection on the patch tokens (cls row skipped through the TMA x offset)
     void* proj = c.ar.alloc((size_t)B * gh * gw * R * 2);
     {
       GemmOp op;
       op.A = taps[k]; op.B = B; op.Ht = 1; op.Wt = N; op.C = F; op.xoff = 1;
       op.Wt_ptr = pw->ptr; op.N = R; op.kpad = (int)pw->shape[1];
-      op.bias = (const float*)pb->ptr; op.out = proj;
+      op.bias = (const float*)pb->ptr; op.out = proj; op.label = "proj1x1";
       add_gemm(c, op);
     }
     void* res = proj;
@@ -512,7 +551,7 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
         op.Wt_ptr = (const char*)uw->ptr + (size_t)sub * rows_per_sub * kpad * 2;
         op.N = R; op.kpad = kpad;
         op.bias = (const float*)ub->ptr; op.out = res;
-        op.so = s; op.oy = sub / s; op.ox = sub % s; op.OH = rh; op.OW = rw;
+        op.so = s; op.oy = sub / s; op.ox = sub % s; op.OH = rh; op.OW = rw; op.label = "convT";
         add_gemm(c, op);
       }
     } else if (k == 3) {
@@ -526,7 +565,7 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
       if (!c.dry) {
         const int is_bf16 = c.is_bf16, nsm = c.num_sms;
         const void* pin = proj;
-        c.launches->push_back([=](cudaStream_t s) {
+        c.add("im2col_3x3s2", 0.0, (double)B * rh * rw * 9 * cpad * 2.0 * 2.0, [=](cudaStream_t s) {
           const long long total = (long long)B * rh * rw * 9 * (cpad / 8);
           const int grid = ew_grid(total, 256, nsm);
           DISPATCH_T(is_bf16, (im2col_3x3s2_kernel<T><<<grid, 256, 0, s>>>((const T*)pin, (T*)col, B, gh, gw, R, cpad)));
@@ -536,7 +575,7 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
       GemmOp op;
       op.A = col; op.B = 1; op.Ht = 1; op.Wt = B * rh * rw; op.C = 9 * cpad;
       op.Wt_ptr = dw->ptr; op.N = R; op.kpad = 9 * cpad;
-      op.bias = (const float*)db->ptr; op.out = res;
+      op.bias = (const float*)db->ptr; op.out = res; op.label = "conv3x3s2";
       add_gemm(c, op);
     }
     {
@@ -546,6 +585,7 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
       op.Wt_ptr = fw->ptr; op.N = C; op.taps = 9; op.kpad = (int)fw->shape[1] / 9;
       op.out = maps[k];
       op.out2_relu = maps_relu ? maps_relu[k] : nullptr;
+      op.label = "fuse3x3";
       add_gemm(c, op);
     }
     c.ar.reset(mk2);
@@ -582,6 +622,7 @@ bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu
   for (int lvl = 3; lvl >= 0 && c.ok; --lvl) {
     const int h = hs[lvl], w = ws[lvl];
     const std::string pre = "fus" + std::to_string(lvl) + ".";
+    c.scope = pre;
     const void* r = maps[lvl];
     const void* r_relu = maps_relu_in ? maps_relu_in[lvl] : nullptr;
     if (!r_relu) {
@@ -597,6 +638,8 @@ bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu
       op.Wt_ptr = ww->ptr; op.N = C; op.taps = 9; op.kpad = (int)ww->shape[1] / 9;
       op.bias = (const float*)bb->ptr; op.act = act; op.out = out; op.add1 = add1; op.add2 = add2;
       op.out2_relu = out_relu;
+      const std::string lab = wn.substr(pre.size());
+      op.label = lab.c_str();
       add_gemm(c, op);
     };
     const void* t = r;
@@ -617,7 +660,7 @@ bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu
       GemmOp op;
       op.A = v_buf; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
       op.Wt_ptr = ww->ptr; op.N = C; op.taps = 1; op.kpad = (int)ww->shape[1];
-      op.bias = (const float*)bb->ptr; op.out = w_buf;
+      op.bias = (const float*)bb->ptr; op.out = w_buf; op.label = "out1x1";
       add_gemm(c, op);
     }
     void* up = lvl == 0 ? fused : f_bufs[lvl & 1];
@@ -648,7 +691,8 @@ bool build_head(Ctx& c, const void* fused, void* depth, int B, int gh, int gw) {
     GemmOp op;
     op.A = fused; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
     op.Wt_ptr = w1->ptr; op.N = C2; op.taps = 9; op.kpad = (int)w1->shape[1] / 9;
-    op.bias = (const float*)b1->ptr; op.out = h1;
+    op.bias = (const float*)b1->ptr; op.out = h1; op.label = "c1";
+    c.scope = "head.";
     add_gemm(c, op);
   }
   add_resize(c, h1, h2, B, h, w, OH, OW, C2);
@@ -660,6 +704,7 @@ bool build_head(Ctx& c, const void* fused, void* depth, int B, int gh, int gw) {
     op.head_w = (const float*)w3->ptr;        // host memory (see dpt_set_weight: "*_host" names are copied)
     op.head_b = *(const float*)b3->ptr;
     op.head_act = cfg.is_metric ? ACT_SIGMOID : ACT_RELU;
+    op.label = "c2c3";
     add_gemm(c, op);
   }
   c.ar.reset(mk);
@@ -714,14 +759,33 @@ Ctx make_ctx(dpt_model_s* m, void* ws, size_t ws_bytes, std::vector<LaunchFn>* l
 
 int run_launches(dpt_model_s* m, std::vector<LaunchFn>& launches, cudaStream_t s, std::string& err) {
   int n = 0;
+  const bool prof = m && m->profiling;
+  if (prof) {
+    // one event before every launch + one after the last; durations are read back by dpt_profile_get
+    while (m->events.size() < launches.size() + 1) {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess) { err = "cudaEventCreate failed"; return DPT_ERR_CUDA; }
+      m->events.push_back(ev);
+    }
+    m->prof_labels.clear();
+    m->prof_flops.clear();
+    m->prof_bytes.clear();
+  }
   for (auto& f : launches) {
+    if (prof) {
+      cudaEventRecord(m->events[n], s);
+      m->prof_labels.push_back(f.label);
+      m->prof_flops.push_back(f.flops);
+      m->prof_bytes.push_back(f.bytes);
+    }
     cudaError_t e = f(s);
     if (e != cudaSuccess) {
-      err = std::string("kernel launch failed: ") + cudaGetErrorString(e);
+      err = std::string("kernel launch failed (") + f.label + "): " + cudaGetErrorString(e);
       return DPT_ERR_CUDA;
     }
     ++n;
   }
+  if (prof) cudaEventRecord(m->events[n], s);
   if (m) m->last_launches = n;
   return DPT_OK;
 }
@@ -775,7 +839,34 @@ int dpt_create(const dpt_config* cfg, dpt_handle* out) {
   return DPT_OK;
 }
 
-void dpt_destroy(dpt_handle h) { delete h; }
+void dpt_destroy(dpt_handle h) {
+  if (!h) return;
+  for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
+  delete h;
+}
+
+int dpt_profile_enable(dpt_handle h, int on) {
+  if (!h) return DPT_ERR_INVALID;
+  h->profiling = on != 0;
+  return DPT_OK;
+}
+
+int dpt_profile_count(dpt_handle h) { return h ? (int)h->prof_labels.size() : 0; }
+
+int dpt_profile_get(dpt_handle h, int i, char* label, int label_len, double* ms, double* flops, double* bytes) {
+  if (!h || i < 0 || i >= (int)h->prof_labels.size() || (size_t)i + 1 >= h->events.size() + 0 + 1) return DPT_ERR_INVALID;
+  float t = 0.f;
+  cudaError_t e = cudaEventElapsedTime(&t, h->events[i], h->events[i + 1]);
+  if (e != cudaSuccess) { h->err = std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
+  if (label && label_len > 0) {
+    strncpy(label, h->prof_labels[i].c_str(), label_len - 1);
+    label[label_len - 1] = 0;
+  }
+  if (ms) *ms = t;
+  if (flops) *flops = h->prof_flops[i];
+  if (bytes) *bytes = h->prof_bytes[i];
+  return DPT_OK;
+}
 
 const char* dpt_last_error(dpt_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
 const char* dpt_op_last_error(void) { return g_err.c_str(); }

@@ -276,6 +276,23 @@ class DPTModel(torch.nn.Module):
     def last_launch_count(self) -> int:
         return int(N.lib().dpt_last_launch_count(self._handle))
 
+    def enable_profiling(self, on: bool = True) -> None:
+        """per-launch CUDA-event timing inside the library (dpt_profile_enable)"""
+        self._require_ready()
+        N.check(N.lib().dpt_profile_enable(self._handle, int(on)), self._handle, "dpt_profile_enable")
+
+    def read_profile(self) -> list[tuple[str, float, float, float]]:
+        """[(label, ms, algorithmic flops, algorithmic bytes)] of the last forward; call after a synchronize"""
+        L = N.lib()
+        out = []
+        buf = C.create_string_buffer(128)
+        ms, fl, by = C.c_double(), C.c_double(), C.c_double()
+        for i in range(L.dpt_profile_count(self._handle)):
+            N.check(L.dpt_profile_get(self._handle, i, buf, 128, C.byref(ms), C.byref(fl), C.byref(by)),
+                    self._handle, "dpt_profile_get")
+            out.append((buf.value.decode(), ms.value, fl.value, by.value))
+        return out
+
     def inference(self, image_bgr, max_side_length=None, use_square_sizing=True) -> torch.Tensor:
         """DPTModel.inference (dpt_model.py:87-109)"""
         with torch.inference_mode():

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 REL_L2 = {torch.bfloat16: 1.5e-2, torch.float16: 3e-3}
-DEPTH_MAXREL = {torch.bfloat16: 5e-2, torch.float16: 1e-2}
+DEPTH_MAXREL = {torch.bfloat16: 3e-2, torch.float16: 5e-3}
 
 
 def _load_model(sd, dtype, name="depth_anything_v2_synth.pth"):
@@ -34,7 +34,9 @@ def _err(a, b):
     a, b = a.float().cpu(), b.float().cpu()
     rel_l2 = ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
     max_abs = (a - b).abs().max().item()
-    max_rel = ((a - b).abs() / b.abs().clamp_min(1e-3 * b.abs().max().item() + 1e-12)).max().item()
+    # max error relative to the largest reference magnitude (depth maps contain values near 0 after the final ReLU,
+    # where an element-wise ratio is meaningless)
+    max_rel = max_abs / (b.abs().max().item() + 1e-12)
     return rel_l2, max_abs, max_rel
 
 

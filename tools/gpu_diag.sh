@@ -7,10 +7,10 @@ OUT=gpurun_out/diag.txt
 : > $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv >> $OUT 2>&1
 FILES="${@:-tests/test_ops_gpu.py tests/test_model_gpu.py}"
-IDS=$(python -m pytest $FILES --collect-only -q -m gpu 2>/dev/null | grep '::')
+IDS=$(python -m pytest $FILES --collect-only -q -m gpu 2>/dev/null | grep '::' | sed 's/\[.*//' | awk '!seen[$0]++')
 for id in $IDS; do
   echo "=== $id" >> $OUT
-  timeout 300 python -m pytest "$id" -x -q -s -m gpu 2>&1 | grep -vE '^$|^=+ .* =+$|^platform|^rootdir|^plugins|^collected' | tail -25 >> $OUT
+  timeout 300 python -m pytest "$id" -q -s -m gpu 2>&1 | grep -vE '^$|^=+ .* =+$|^platform|^rootdir|^plugins|^collected' | tail -40 >> $OUT
   echo "--- exit ${PIPESTATUS[0]}" >> $OUT
 done
 grep -cE '^--- exit 0' $OUT | xargs echo "passed:" | tee -a $OUT
