@@ -99,9 +99,10 @@ int dpt_head(dpt_handle h, const void* fused, void* depth, void* workspace, size
 int dpt_op_conv_gemm(const void* A, const void* Wt, const float* bias, void* out, const void* add1, const void* add2,
                      void* out_relu, int B, int H, int W, int C, int N, int taps, int xoff, int act, int out_f32,
                      int dtype, void* stream);
-/* O = softmax(scale * Q K^T + bias) V, qkv [B,N,3F] 16-bit (F = heads*64), out [B,N,F]; bias [heads,N,N] or NULL */
-int dpt_op_attention(const void* qkv, const void* bias, void* out, int B, int N, int heads, float scale, int dtype,
-                     void* stream);
+/* O = softmax(scale * Q K^T + bias) V, qkv [B,N,3F] 16-bit (F = heads*64), out [B,N,F]; bias [heads,N,bias_ld]
+ * 16-bit with bias_ld a multiple of 128 (>= N), or NULL */
+int dpt_op_attention(const void* qkv, const void* bias, int64_t bias_ld, void* out, int B, int N, int heads,
+                     float scale, int dtype, void* stream);
 /* y = LayerNorm(x) * w + b, x [M,F] f32, y [M,F] 16-bit */
 int dpt_op_layernorm(const float* x, const float* w, const float* b, void* y, int64_t M, int F, float eps, int dtype,
                      void* stream);

@@ -38,9 +38,41 @@ struct __align__(64) AttnParams {
   float scale_log2;   // softmax scale * log2(e)
   void* out;          // [B, N, F] 16-bit
   const void* bias;   // optional additive bias [H, N, ldb] 16-bit (BEiT relative position bias), shared over batch
-  long long ldb;      // row stride of bias in elements
+  long long ldb;      // row stride of bias in elements: a multiple of 128 (whole kv tiles stay in bounds)
 };
 
+// 32 consecutive 16-bit bias values (64 B, 16-byte aligned) -> fp32, pre-multiplied by log2(e)
+DPT_DEVICE void load_bias32(const uint16_t* src, float (&bf)[32], int is_bf16) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint4 u = __ldg(s4 + k);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack2(w[t], is_bf16);
+      bf[8 * k + 2 * t] = f.x * 1.4426950408889634f;
+      bf[8 * k + 2 * t + 1] = f.y * 1.4426950408889634f;
+    }
+  }
+}
+
+// o_acc = o_acc * alpha + O_tile (64 fp32 columns of this thread's TMEM lane)
+DPT_DEVICE void fold_o(uint32_t o_addr, float2 (&o_acc)[ATT_D / 2], float alpha) {
+  const float2 a2 = make_float2(alpha, alpha);
+#pragma unroll
+  for (int cc = 0; cc < ATT_D; cc += 32) {
+    uint32_t v[32];
+    tmem_ld32(o_addr + cc, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      o_acc[cc / 2 + i] = __ffma2_rn(o_acc[cc / 2 + i], a2,
+                                     make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
+  }
+}
+
+template <bool HAS_BIAS>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -169,82 +201,103 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const int is_bf16 = p.is_bf16;
     const float c = p.scale_log2;
-    float m_run = -INFINITY;   // running max of raw scores (scaled by c lazily)
-    float l_run = 0.0f;
+    const float2 c2 = make_float2(c, c);
+    float m_run = -INFINITY;   // running max, in exp2 units (score * scale * log2e [+ bias * log2e])
+    float2 l_run2 = make_float2(0.0f, 0.0f);
     float alpha_prev = 1.0f;
-    float o_acc[ATT_D];
+    float2 o_acc[ATT_D / 2];
 #pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.0f;
+    for (int i = 0; i < ATT_D / 2; ++i) o_acc[i] = make_float2(0.0f, 0.0f);
     const int qrow = q0 + r;
     const uint16_t* bias_row = nullptr;
-    if (p.bias != nullptr && qrow < p.N)
-      bias_row = reinterpret_cast<const uint16_t*>(p.bias) + ((long long)h * p.N + qrow) * p.ldb;
+    if constexpr (HAS_BIAS) {
+      // rows past N read row N-1 (their results are never stored); ldb is a multiple of ATT_BN so whole tiles are
+      // in bounds
+      bias_row = reinterpret_cast<const uint16_t*>(p.bias) + ((long long)h * p.N + min(qrow, p.N - 1)) * p.ldb;
+    }
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv0 = j * ATT_BN;
       const bool tail = (kv0 + ATT_BN > p.N);
-      // ---- pass 1: row max (in units of score*c, bias*log2e folded in)
+      // ---- pass 1: row max
       float m_tile = -INFINITY;
 #pragma unroll 1
       for (int cc = 0; cc < ATT_BN; cc += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_addr + cc, v);
         tmem_ld_wait();
+        if constexpr (HAS_BIAS) {
+          float bf[32];
+          load_bias32(bias_row + kv0 + cc, bf, is_bf16);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sv = __uint_as_float(v[i]) * c;
-          if (bias_row != nullptr && kv0 + cc + i < p.N) {
-            const uint16_t raw = bias_row[kv0 + cc + i];
-            const float bv = is_bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw))
-                                     : __half2float(*reinterpret_cast<const __half*>(&raw));
-            sv = fmaf(bv, 1.4426950408889634f, sv);
-          }
-          if (tail && kv0 + cc + i >= p.N) sv = -INFINITY;
-          m_tile = fmaxf(m_tile, sv);
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), c, bf[i]));
         }
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + cc + i >= p.N) v[i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
       }
+      if constexpr (!HAS_BIAS) m_tile *= c;  // max(c*s) = c*max(s), c > 0
       const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = exp2f(m_run - m_new);  // first tile: exp2(-inf) = 0
-      // ---- wait until the previous P@V has consumed the P buffer, then fold O_{j-1} later
+      const float alpha = ex2_approx(m_run - m_new);  // first tile: exp2(-inf) = 0
+      const float2 neg_m2 = make_float2(-m_new, -m_new);
+      // ---- the previous P@V must have consumed the P buffer before it is overwritten
       if (j > 0) mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-      // ---- pass 2: P = exp2(s - m_new), row sum, 16-bit P -> swizzled smem
-      float l_tile = 0.0f;
+      // ---- pass 2: P = exp2(s*c - m_new), row sum, 16-bit P -> swizzled smem
+      float2 l_tile2 = make_float2(0.0f, 0.0f);
 #pragma unroll 1
       for (int cc = 0; cc < ATT_BN; cc += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_addr + cc, v);
         tmem_ld_wait();
-        float pf[32];
+        float2 pf[16];
+        if constexpr (HAS_BIAS) {
+          float bf[32];
+          load_bias32(bias_row + kv0 + cc, bf, is_bf16);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sv = __uint_as_float(v[i]) * c;
-          if (bias_row != nullptr && kv0 + cc + i < p.N) {
-            const uint16_t raw = bias_row[kv0 + cc + i];
-            const float bv = is_bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw))
-                                     : __half2float(*reinterpret_cast<const __half*>(&raw));
-            sv = fmaf(bv, 1.4426950408889634f, sv);
+          for (int i = 0; i < 16; ++i) {
+            const float2 sv = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2,
+                                         make_float2(bf[2 * i], bf[2 * i + 1]));
+            pf[i] = __fadd2_rn(sv, neg_m2);
           }
-          float pv = exp2f(sv - m_new);
-          if (tail && kv0 + cc + i >= p.N) pv = 0.0f;
-          pf[i] = pv;
-          l_tile += pv;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pf[i] = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, neg_m2);
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pf[i].x = ex2_approx(pf[i].x);
+          pf[i].y = ex2_approx(pf[i].y);
+        }
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (kv0 + cc + 2 * i >= p.N) pf[i].x = 0.0f;
+            if (kv0 + cc + 2 * i + 1 >= p.N) pf[i].y = 0.0f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) l_tile2 = __fadd2_rn(l_tile2, pf[i]);
         uint8_t* chunk_base = sP + (cc >> 6) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int lch = ((cc & 63) >> 3) + ch;
-          const int phys = lch ^ (r & 7);
+          const int phys = (((cc & 63) >> 3) + ch) ^ (r & 7);
           uint4 o;
-          o.x = pack2(pf[8 * ch + 0], pf[8 * ch + 1], is_bf16);
-          o.y = pack2(pf[8 * ch + 2], pf[8 * ch + 3], is_bf16);
-          o.z = pack2(pf[8 * ch + 4], pf[8 * ch + 5], is_bf16);
-          o.w = pack2(pf[8 * ch + 6], pf[8 * ch + 7], is_bf16);
+          o.x = pack2(pf[4 * ch + 0].x, pf[4 * ch + 0].y, is_bf16);
+          o.y = pack2(pf[4 * ch + 1].x, pf[4 * ch + 1].y, is_bf16);
+          o.z = pack2(pf[4 * ch + 2].x, pf[4 * ch + 2].y, is_bf16);
+          o.w = pack2(pf[4 * ch + 3].x, pf[4 * ch + 3].y, is_bf16);
           *reinterpret_cast<uint4*>(chunk_base + phys * 16) = o;
         }
       }
-      l_run = l_run * alpha + l_tile;
+      l_run2 = __ffma2_rn(l_run2, make_float2(alpha, alpha), l_tile2);
       m_run = m_new;
       // make P visible to the tensor core (async proxy) and release S
       fence_proxy_async_smem();
@@ -253,15 +306,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       // ---- fold O_{j-1} (scaled by the alpha of step j-1) while the tensor core works on S_{j+1}, P_j V_j
       if (j > 0) {
         tc_fence_after();
-        const uint32_t o_addr = tmem_O + lane_addr + ((j - 1) & 1) * ATT_D;
-#pragma unroll
-        for (int cc = 0; cc < ATT_D; cc += 32) {
-          uint32_t v[32];
-          tmem_ld32(o_addr + cc, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[cc + i] = fmaf(o_acc[cc + i], alpha_prev, __uint_as_float(v[i]));
-        }
+        fold_o(tmem_O + lane_addr + ((j - 1) & 1) * ATT_D, o_acc, alpha_prev);
       }
       alpha_prev = alpha;
     }
@@ -270,26 +315,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       const int j = n_kv - 1;
       mbar_wait(&o_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t o_addr = tmem_O + lane_addr + (j & 1) * ATT_D;
-#pragma unroll
-      for (int cc = 0; cc < ATT_D; cc += 32) {
-        uint32_t v[32];
-        tmem_ld32(o_addr + cc, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[cc + i] = fmaf(o_acc[cc + i], alpha_prev, __uint_as_float(v[i]));
-      }
+      fold_o(tmem_O + lane_addr + (j & 1) * ATT_D, o_acc, alpha_prev);
     }
     if (qrow < p.N) {
-      const float inv_l = 1.0f / l_run;
+      const float inv_l = 1.0f / (l_run2.x + l_run2.y);
       uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)b * p.N + qrow) * p.F + h * ATT_D;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         uint4 o;
-        o.x = pack2(o_acc[8 * ch + 0] * inv_l, o_acc[8 * ch + 1] * inv_l, is_bf16);
-        o.y = pack2(o_acc[8 * ch + 2] * inv_l, o_acc[8 * ch + 3] * inv_l, is_bf16);
-        o.z = pack2(o_acc[8 * ch + 4] * inv_l, o_acc[8 * ch + 5] * inv_l, is_bf16);
-        o.w = pack2(o_acc[8 * ch + 6] * inv_l, o_acc[8 * ch + 7] * inv_l, is_bf16);
+        o.x = pack2(o_acc[4 * ch + 0].x * inv_l, o_acc[4 * ch + 0].y * inv_l, is_bf16);
+        o.y = pack2(o_acc[4 * ch + 1].x * inv_l, o_acc[4 * ch + 1].y * inv_l, is_bf16);
+        o.z = pack2(o_acc[4 * ch + 2].x * inv_l, o_acc[4 * ch + 2].y * inv_l, is_bf16);
+        o.w = pack2(o_acc[4 * ch + 3].x * inv_l, o_acc[4 * ch + 3].y * inv_l, is_bf16);
         *reinterpret_cast<uint4*>(orow + 8 * ch) = o;
       }
     }

@@ -159,20 +159,29 @@ bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
 
 int pick_block_n(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
-template <int BN>
-cudaError_t launch_gemm_bn(const GemmParams& p, int grid, cudaStream_t s) {
+template <int BN, int OUT_KIND, int ACT>
+cudaError_t launch_gemm_inst(const GemmParams& p, int grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmCfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(p);
+  gemm_tc_kernel<BN, OUT_KIND, ACT><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(p);
   return cudaGetLastError();
 }
 
+template <int BN>
+cudaError_t launch_gemm_bn(const GemmParams& p, int grid, cudaStream_t s) {
+  if (p.out_kind == OUT_F32) return launch_gemm_inst<BN, OUT_F32, ACT_NONE>(p, grid, s);
+  if (p.act == ACT_GELU) return launch_gemm_inst<BN, OUT_HALF, ACT_GELU>(p, grid, s);
+  if (p.act == ACT_RELU) return launch_gemm_inst<BN, OUT_HALF, ACT_RELU>(p, grid, s);
+  return launch_gemm_inst<BN, OUT_HALF, ACT_NONE>(p, grid, s);
+}
+
 cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, cudaStream_t s) {
+  if (p.out_kind == OUT_HEAD) return launch_gemm_inst<32, OUT_HEAD, ACT_NONE>(p, grid, s);
   switch (bn) {
     case 32: return launch_gemm_bn<32>(p, grid, s);
     case 64: return launch_gemm_bn<64>(p, grid, s);
@@ -216,6 +225,8 @@ bool add_gemm(Ctx& c, GemmOp op) {
   if (op.kpad == 0) op.kpad = (op.C + 63) / 64 * 64;
   if (op.C % 8 != 0) return c.fail("gemm: channel count must be a multiple of 8");
   if (op.out_kind != OUT_HEAD && op.N % 8 != 0) return c.fail("gemm: N must be a multiple of 8");
+  if (op.out_kind == OUT_F32 && op.act != ACT_NONE) return c.fail("gemm: fp32 output has no activation variant");
+  if (op.act == ACT_SIGMOID) return c.fail("gemm: sigmoid is only available in head mode");
   if (c.dry) return true;
 
   GemmParams p;
@@ -285,7 +296,23 @@ bool add_gemm(Ctx& c, GemmOp op) {
   return true;
 }
 
-bool add_attention(Ctx& c, const void* qkv, const void* bias, void* out, int B, int N, int heads, float scale) {
+template <bool HAS_BIAS>
+cudaError_t launch_attn(const AttnParams& p, dim3 grid, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ATT_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  attn_tc_kernel<HAS_BIAS><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
+  return cudaGetLastError();
+}
+
+// bias (optional): [heads, N, ldb] 16-bit with ldb a multiple of 128
+bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, void* out, int B, int N, int heads,
+                   float scale) {
+  if (bias != nullptr && (ldb % ATT_BN != 0 || ldb < N)) return c.fail("attention: bias row stride must be a multiple of 128");
   if (c.dry) return true;
   AttnParams p;
   memset(&p, 0, sizeof p);
@@ -299,19 +326,13 @@ bool add_attention(Ctx& c, const void* qkv, const void* bias, void* out, int B, 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out;
   p.bias = bias;
-  p.ldb = N;
+  p.ldb = ldb;
   dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
+  const bool has_bias = bias != nullptr;
   c.add("attn:" + c.scope, 4.0 * B * heads * (double)N * N * 64.0, 4.0 * (double)B * N * F * 2.0,
-        [p, grid](cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
-  });
+        [p, grid, has_bias](cudaStream_t s) {
+          return has_bias ? launch_attn<true>(p, grid, s) : launch_attn<false>(p, grid, s);
+        });
   return true;
 }
 
@@ -477,7 +498,7 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       op.bias = (const float*)qb->ptr; op.out = qkv; op.label = "qkv";
       add_gemm(c, op);
     }
-    add_attention(c, qkv, nullptr, att, B, N, heads, scale);
+    add_attention(c, qkv, nullptr, 0, att, B, N, heads, scale);
     {
       GemmOp op;  // x += (gamma1 . proj)(att)   (LayerScale folded into the packed weights)
       op.A = att; op.Wt = (int)M; op.C = F; op.Wt_ptr = pw->ptr; op.N = F; op.kpad = (int)pw->shape[1];
@@ -993,12 +1014,12 @@ int dpt_op_conv_gemm(const void* A, const void* Wt, const float* bias, void* out
   return run_op(c, launches, stream);
 }
 
-int dpt_op_attention(const void* qkv, const void* bias, void* out, int B, int N, int heads, float scale, int dtype,
-                     void* stream) {
+int dpt_op_attention(const void* qkv, const void* bias, int64_t bias_ld, void* out, int B, int N, int heads,
+                     float scale, int dtype, void* stream) {
   std::vector<LaunchFn> launches;
   Ctx c = make_ctx(nullptr, nullptr, 0, &launches, false);
   c.is_bf16 = dtype == DPT_BF16;
-  add_attention(c, qkv, bias, out, B, N, heads, scale);
+  add_attention(c, qkv, bias, bias_ld, out, B, N, heads, scale);
   return run_op(c, launches, stream);
 }
 

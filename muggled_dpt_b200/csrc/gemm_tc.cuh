@@ -66,8 +66,9 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + BAR_BYTES;
+  static constexpr int BAR_BYTES = 256 + 2 * BLOCK_N * 4;  // mbarriers + tmem ptr, bias tile [2][BLOCK_N]
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
 };
 
@@ -110,17 +111,19 @@ DPT_DEVICE float2 unpack2(uint32_t u, int is_bf16) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int OUT_KIND, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // no static shared memory in this kernel: the dynamic segment starts at the CTA's (1024-aligned) window base;
+  // checked below because the 128B-swizzle descriptors depend on it
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
   uint8_t* staging = smem_b + STAGES * Cfg::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);  // [2][BLOCK_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BLOCK_N);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -135,6 +138,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int num_kb = p.num_taps * p.kchunks;
 
   if (warp_idx == 0 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("dpt gemm: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
     for (int i = 0; i < STAGES; ++i) {
@@ -218,6 +225,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else {
     // ===================================== epilogue =====================================
     const int ew = warp_idx - 2;      // 0..7
+    const int et = threadIdx.x - 64;  // 0..255
     const int q = warp_idx & 3;       // TMEM lane quarter this warp may read
     const int wg = ew >> 2;           // column half
     constexpr int COLS_PER_WG = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
@@ -226,6 +234,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int TW = 1 << p.tw_log2, TH = GEMM_BLOCK_M >> p.tw_log2;
     const int is_bf16 = p.is_bf16;
     const int r = q * 32 + lane;  // accumulator row (TMEM lane) owned by this thread
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -242,61 +251,74 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const bool row_ok = (x < p.W) && (y < p.H);
       const long long pix = ((long long)b * p.OH + (long long)y * p.so + p.oy) * p.OW + (long long)x * p.so + p.ox;
 
+      // bias of this n-tile -> smem (zero beyond N / without bias); double-buffered by accumulator stage
+      float* bs = bias_s + as * BLOCK_N;
+      if (et < BLOCK_N) {
+        const int n = n_blk * BLOCK_N + et;
+        bs[et] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+      }
+      named_bar_sync(1, GEMM_EPI_WARPS * 32);
+
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
 
       if (wg_active) {
         const int col_base = wg * COLS_PER_WG;  // within the tile
-        if (p.out_kind == OUT_HEAD) {
-          if constexpr (BLOCK_N == 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N, v);
-            tmem_ld_wait();
-            float acc = p.head_b;
+        const uint32_t t_acc = tmem_base + lane_addr + as * BLOCK_N + col_base;
+        if constexpr (OUT_KIND == OUT_HEAD) {
+          uint32_t v[32];
+          tmem_ld32(t_acc, v);
+          tmem_ld_wait();
+          float acc = p.head_b;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float t = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.0f);
-              acc = fmaf(fmaxf(t, 0.0f), p.head_w[j], acc);
-            }
-            acc = apply_act(acc, p.head_act);
-            if (row_ok) {
-              if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.ldo] = __float2bfloat16_rn(acc);
-              else reinterpret_cast<__half*>(p.out)[pix * p.ldo] = __float2half_rn(acc);
-            }
+          for (int j = 0; j < 32; ++j) acc = fmaf(fmaxf(__uint_as_float(v[j]) + bs[j], 0.0f), p.head_w[j], acc);
+          acc = p.head_act == ACT_SIGMOID ? 1.0f / (1.0f + __expf(-acc)) : fmaxf(acc, 0.0f);
+          if (row_ok) {
+            if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.ldo] = __float2bfloat16_rn(acc);
+            else reinterpret_cast<__half*>(p.out)[pix * p.ldo] = __float2half_rn(acc);
           }
         } else {
-          const bool f32out = p.out_kind == OUT_F32;
-          // staging chunk = 128 B per row: 64 16-bit columns or 32 fp32 columns
-          const int cols_per_stg = f32out ? 32 : 64;
-          for (int c0 = 0; c0 < COLS_PER_WG; c0 += cols_per_stg) {
-            const int ncols_here = min(cols_per_stg, COLS_PER_WG - c0);
-            // ---- phase 1: my row, ncols_here columns -> staging (swizzled 16-byte chunks)
+          constexpr bool F32OUT = OUT_KIND == OUT_F32;
+          constexpr int COLS_PER_STG = F32OUT ? 32 : 64;  // staging row = 128 B
+          constexpr int ELEMS_PER_CHUNK = F32OUT ? 4 : 8;
+          constexpr int NCOLS_HERE = COLS_PER_STG < COLS_PER_WG ? COLS_PER_STG : COLS_PER_WG;
+          const int sub = lane & 7;  // 16-byte chunk within a 128-byte row segment (phase 2)
 #pragma unroll 1
-            for (int cc = 0; cc < ncols_here; cc += 32) {
-              const int tcol = col_base + c0 + cc;
+          for (int c0 = 0; c0 < COLS_PER_WG; c0 += COLS_PER_STG) {
+            // ---- phase 1: my row, NCOLS_HERE columns: TMEM -> +bias, activation -> swizzled staging
+#pragma unroll
+            for (int cc = 0; cc < NCOLS_HERE; cc += 32) {
               uint32_t v[32];
-              tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + tcol, v);
+              tmem_ld32(t_acc + c0 + cc, v);
               tmem_ld_wait();
-              const int ncol = n_blk * BLOCK_N + tcol;
+              const float4* b4 = reinterpret_cast<const float4*>(bs + col_base + c0 + cc);
               float f[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float t = __uint_as_float(v[j]);
-                if (p.bias != nullptr && ncol + j < p.N) t += __ldg(p.bias + ncol + j);
-                f[j] = apply_act(t, p.act);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = b4[j];
+                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
               }
-              if (f32out) {
+              if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              } else if constexpr (ACT == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+              }
+              if constexpr (F32OUT) {
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                   const int phys = ch ^ (lane & 7);
-                  float4 o = make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
-                  *reinterpret_cast<float4*>(stg + lane * 128 + phys * 16) = o;
+                  *reinterpret_cast<float4*>(stg + lane * 128 + phys * 16) =
+                      make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
                 }
               } else {
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
-                  const int lch = (cc >> 3) + ch;  // logical 16-byte chunk within the 128-byte row
-                  const int phys = lch ^ (lane & 7);
+                  const int phys = ((cc >> 3) + ch) ^ (lane & 7);
                   uint4 o;
                   o.x = pack2(f[8 * ch + 0], f[8 * ch + 1], is_bf16);
                   o.y = pack2(f[8 * ch + 2], f[8 * ch + 3], is_bf16);
@@ -307,66 +329,77 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               }
             }
             __syncwarp();
-            // ---- phase 2: coalesced global IO; 8 lanes cover one 128-byte row segment, 4 rows per pass
+            // ---- phase 2: coalesced global IO; 8 lanes cover one 128-byte row segment, 4 rows per pass, all
+            //      eight passes' loads issued before the first store (the residual may alias the output)
             const int ncol0 = n_blk * BLOCK_N + col_base + c0;  // first output column of this staging chunk
-            const int sub = lane & 7;                           // 16-byte chunk within the row segment
-            const int elems_per_chunk = f32out ? 4 : 8;
-            const bool col_ok = (sub * elems_per_chunk < ncols_here) && (ncol0 + sub * elems_per_chunk) < p.N;
-#pragma unroll 1
-            for (int rr0 = 0; rr0 < 32; rr0 += 4) {
-              const int rr = rr0 + (lane >> 3);
-              const long long rpix = __shfl_sync(0xffffffffu, pix, rr);
-              const int rok = __shfl_sync(0xffffffffu, (int)row_ok, rr);
-              if (rok && col_ok) {
-                const int phys = sub ^ (rr & 7);
-                uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + phys * 16);
-                const long long coff = ncol0 + sub * elems_per_chunk;
-                if (f32out) {
-                  float4 o = *reinterpret_cast<float4*>(&val);
-                  if (p.add1) {
-                    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add1) +
-                                                                      rpix * p.ld_add1 + coff);
-                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-                  }
-                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + rpix * p.ldo + coff) = o;
-                } else {
-                  if (p.add1 || p.add2 || p.out2_relu) {
-                    float2 f0 = unpack2(val.x, is_bf16), f1 = unpack2(val.y, is_bf16);
-                    float2 f2 = unpack2(val.z, is_bf16), f3 = unpack2(val.w, is_bf16);
-                    if (p.add1) {
-                      const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add1) +
-                                                                      rpix * p.ld_add1 + coff);
-                      float2 g;
-                      g = unpack2(a.x, is_bf16); f0.x += g.x; f0.y += g.y;
-                      g = unpack2(a.y, is_bf16); f1.x += g.x; f1.y += g.y;
-                      g = unpack2(a.z, is_bf16); f2.x += g.x; f2.y += g.y;
-                      g = unpack2(a.w, is_bf16); f3.x += g.x; f3.y += g.y;
-                    }
-                    if (p.add2) {
-                      const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add2) +
-                                                                      rpix * p.ld_add2 + coff);
-                      float2 g;
-                      g = unpack2(a.x, is_bf16); f0.x += g.x; f0.y += g.y;
-                      g = unpack2(a.y, is_bf16); f1.x += g.x; f1.y += g.y;
-                      g = unpack2(a.z, is_bf16); f2.x += g.x; f2.y += g.y;
-                      g = unpack2(a.w, is_bf16); f3.x += g.x; f3.y += g.y;
-                    }
-                    val.x = pack2(f0.x, f0.y, is_bf16);
-                    val.y = pack2(f1.x, f1.y, is_bf16);
-                    val.z = pack2(f2.x, f2.y, is_bf16);
-                    val.w = pack2(f3.x, f3.y, is_bf16);
-                    if (p.out2_relu) {
-                      uint4 rv;
-                      rv.x = pack2(fmaxf(f0.x, 0.f), fmaxf(f0.y, 0.f), is_bf16);
-                      rv.y = pack2(fmaxf(f1.x, 0.f), fmaxf(f1.y, 0.f), is_bf16);
-                      rv.z = pack2(fmaxf(f2.x, 0.f), fmaxf(f2.y, 0.f), is_bf16);
-                      rv.w = pack2(fmaxf(f3.x, 0.f), fmaxf(f3.y, 0.f), is_bf16);
-                      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2_relu) + rpix * p.ld_out2 + coff) = rv;
-                    }
-                  }
-                  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + rpix * p.ldo + coff) = val;
+            const bool col_ok = (sub * ELEMS_PER_CHUNK < NCOLS_HERE) && (ncol0 + sub * ELEMS_PER_CHUNK) < p.N;
+            const long long coff = ncol0 + sub * ELEMS_PER_CHUNK;
+            long long rpix[8];
+            bool ok[8];
+            uint4 val[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              rpix[i] = __shfl_sync(0xffffffffu, pix, rr);
+              ok[i] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
+              val[i] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((sub ^ (rr & 7)) * 16));
+            }
+            if constexpr (F32OUT) {
+              if (p.add1 != nullptr) {
+                float4 a[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  a[i] = ok[i] ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add1) +
+                                                                  rpix[i] * p.ld_add1 + coff)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 o = *reinterpret_cast<float4*>(&val[i]);
+                  o.x += a[i].x; o.y += a[i].y; o.z += a[i].z; o.w += a[i].w;
+                  val[i] = *reinterpret_cast<uint4*>(&o);
                 }
               }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
+            } else {
+              if (p.add1 != nullptr || p.add2 != nullptr || p.out2_relu != nullptr) {
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                uint4 a1[8], a2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  a1[i] = (p.add1 != nullptr && ok[i])
+                              ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add1) +
+                                                                rpix[i] * p.ld_add1 + coff)
+                              : z;
+                  a2[i] = (p.add2 != nullptr && ok[i])
+                              ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add2) +
+                                                                rpix[i] * p.ld_add2 + coff)
+                              : z;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  uint32_t* vv = reinterpret_cast<uint32_t*>(&val[i]);
+                  const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&a1[i]);
+                  const uint32_t* x2 = reinterpret_cast<const uint32_t*>(&a2[i]);
+                  uint4 rv;
+                  uint32_t* rr32 = reinterpret_cast<uint32_t*>(&rv);
+#pragma unroll
+                  for (int w = 0; w < 4; ++w) {
+                    float2 fv = unpack2(vv[w], is_bf16);
+                    const float2 g1 = unpack2(x1[w], is_bf16), g2 = unpack2(x2[w], is_bf16);
+                    fv.x += g1.x + g2.x;
+                    fv.y += g1.y + g2.y;
+                    vv[w] = pack2(fv.x, fv.y, is_bf16);
+                    rr32[w] = pack2(fmaxf(fv.x, 0.f), fmaxf(fv.y, 0.f), is_bf16);
+                  }
+                  if (p.out2_relu != nullptr && ok[i])
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2_relu) + rpix[i] * p.ld_out2 + coff) = rv;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
             }
             __syncwarp();
           }

@@ -43,29 +43,44 @@ DPT_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 DPT_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+  // expires) instead of burning issue slots that the epilogue / softmax warps on the same SM sub-partition need.
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken pipeline traps (-> launch failure reported to the host) instead of hanging the GPU.
-DPT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+// Slow path, kept out of line: a broken pipeline traps (-> launch failure reported to the host) instead of hanging.
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at ~2 GHz
-      printf("dpt: mbarrier wait timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x,
-             smem_u32(bar), parity);
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      printf("dpt: mbarrier wait timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
+             (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
+}
+DPT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
+// named barrier among a subset of the CTA's warps
+DPT_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+DPT_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -32,7 +32,13 @@ def conv_gemm(A, Wt, bias=None, add1=None, add2=None, want_relu=False, taps=1, x
 def attention(qkv, heads, scale, bias=None):
     B, n, F3 = qkv.shape
     out = torch.empty((B, n, F3 // 3), device=qkv.device, dtype=qkv.dtype)
-    rc = N.lib().dpt_op_attention(_p(qkv), _p(bias), _p(out), B, n, heads, float(scale), DT[qkv.dtype], _stream())
+    ld = 0
+    if bias is not None:  # pad rows to a multiple of 128 columns (kernel contract)
+        ld = (n + 127) // 128 * 128
+        padded = torch.zeros((bias.shape[0], n, ld), device=bias.device, dtype=bias.dtype)
+        padded[:, :, :n] = bias
+        bias = padded
+    rc = N.lib().dpt_op_attention(_p(qkv), _p(bias), ld, _p(out), B, n, heads, float(scale), DT[qkv.dtype], _stream())
     N.check(rc, None, "dpt_op_attention")
     torch.cuda.synchronize()
     return out
