@@ -72,7 +72,7 @@ DPT_DEVICE void fold_o(uint32_t o_addr, float2 (&o_acc)[ATT_D / 2], float alpha)
   }
 }
 
-template <bool HAS_BIAS>
+template <bool HAS_BIAS, bool BF16>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
-      const uint32_t idesc_s = make_idesc_f16(128, ATT_BN, p.is_bf16 != 0, false, false);
-      const uint32_t idesc_o = make_idesc_f16(128, ATT_D, p.is_bf16 != 0, false, true);  // V: MN-major B operand
+      const uint32_t idesc_s = make_idesc_f16(128, ATT_BN, BF16, false, false);
+      const uint32_t idesc_o = make_idesc_f16(128, ATT_D, BF16, false, true);  // V: MN-major B operand
       const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ));
       const uint64_t p_desc0 = make_smem_desc_sw128(smem_u32(sP));
       const uint64_t p_desc1 = make_smem_desc_sw128(smem_u32(sP + ATT_TILE_BYTES));
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     const int q = warp_idx & 3;          // TMEM lane quarter
     const int r = q * 32 + lane;         // query row within the tile
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    const int is_bf16 = p.is_bf16;
+    constexpr int is_bf16 = BF16 ? 1 : 0;
     const float c = p.scale_log2;
     const float2 c2 = make_float2(c, c);
     float m_run = -INFINITY;   // running max, in exp2 units (score * scale * log2e [+ bias * log2e])
@@ -216,18 +216,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       bias_row = reinterpret_cast<const uint16_t*>(p.bias) + ((long long)h * p.N + min(qrow, p.N - 1)) * p.ldb;
     }
 
+    uint32_t vbuf[2][32];  // software-pipelined TMEM reads: chunk i+1 is in flight while chunk i is processed
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv0 = j * ATT_BN;
       const bool tail = (kv0 + ATT_BN > p.N);
+      const uint32_t s_addr = tmem_S + lane_addr;
       // ---- pass 1: row max
       float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < ATT_BN; cc += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + cc, v);
-        tmem_ld_wait();
+      tmem_ld32(s_addr, vbuf[0]);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        uint32_t(&v)[32] = vbuf[ci & 1];
+        const int cc = ci * 32;
+        tmem_ld_wait_dep(v);
+        tmem_ld32(s_addr + ((ci + 1) & 3) * 32, vbuf[(ci + 1) & 1]);  // after chunk 3: chunk 0 again, for pass 2
         if constexpr (HAS_BIAS) {
           float bf[32];
           load_bias32(bias_row + kv0 + cc, bf, is_bf16);
@@ -249,52 +253,54 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       const float2 neg_m2 = make_float2(-m_new, -m_new);
       // ---- the previous P@V must have consumed the P buffer before it is overwritten
       if (j > 0) mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+      const uint32_t o_prev_addr = tmem_O + lane_addr + ((j - 1) & 1) * ATT_D;
       // ---- pass 2: P = exp2(s*c - m_new), row sum, 16-bit P -> swizzled smem
       float2 l_tile2 = make_float2(0.0f, 0.0f);
-#pragma unroll 1
-      for (int cc = 0; cc < ATT_BN; cc += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + cc, v);
-        tmem_ld_wait();
-        float2 pf[16];
-        if constexpr (HAS_BIAS) {
-          float bf[32];
-          load_bias32(bias_row + kv0 + cc, bf, is_bf16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 sv = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2,
-                                         make_float2(bf[2 * i], bf[2 * i + 1]));
-            pf[i] = __fadd2_rn(sv, neg_m2);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            pf[i] = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, neg_m2);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          pf[i].x = ex2_approx(pf[i].x);
-          pf[i].y = ex2_approx(pf[i].y);
-        }
-        if (tail) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (kv0 + cc + 2 * i >= p.N) pf[i].x = 0.0f;
-            if (kv0 + cc + 2 * i + 1 >= p.N) pf[i].y = 0.0f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) l_tile2 = __fadd2_rn(l_tile2, pf[i]);
+      for (int ci = 0; ci < 4; ++ci) {
+        uint32_t(&v)[32] = vbuf[ci & 1];
+        const int cc = ci * 32;
+        tmem_ld_wait_dep(v);
+        if (ci + 1 < 4) tmem_ld32(s_addr + (ci + 1) * 32, vbuf[(ci + 1) & 1]);
+        else if (j > 0) tmem_ld32(o_prev_addr, vbuf[0]);  // first half of O_{j-1}, folded after the arrive below
+        float bf[HAS_BIAS ? 32 : 1];
+        if constexpr (HAS_BIAS) load_bias32(bias_row + kv0 + cc, *reinterpret_cast<float(*)[32]>(&bf), is_bf16);
         uint8_t* chunk_base = sP + (cc >> 6) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int phys = (((cc & 63) >> 3) + ch) ^ (r & 7);
-          uint4 o;
-          o.x = pack2(pf[4 * ch + 0].x, pf[4 * ch + 0].y, is_bf16);
-          o.y = pack2(pf[4 * ch + 1].x, pf[4 * ch + 1].y, is_bf16);
-          o.z = pack2(pf[4 * ch + 2].x, pf[4 * ch + 2].y, is_bf16);
-          o.w = pack2(pf[4 * ch + 3].x, pf[4 * ch + 3].y, is_bf16);
-          *reinterpret_cast<uint4*>(chunk_base + phys * 16) = o;
+        for (int hh = 0; hh < 2; ++hh) {  // 16 columns at a time keeps the live register set small
+          float2 pf[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 sv = make_float2(__uint_as_float(v[16 * hh + 2 * i]), __uint_as_float(v[16 * hh + 2 * i + 1]));
+            if constexpr (HAS_BIAS)
+              pf[i] = __fadd2_rn(__ffma2_rn(sv, c2, make_float2(bf[16 * hh + 2 * i], bf[16 * hh + 2 * i + 1])), neg_m2);
+            else
+              pf[i] = __ffma2_rn(sv, c2, neg_m2);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pf[i].x = ex2_approx(pf[i].x);
+            pf[i].y = ex2_approx(pf[i].y);
+          }
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (kv0 + cc + 16 * hh + 2 * i >= p.N) pf[i].x = 0.0f;
+              if (kv0 + cc + 16 * hh + 2 * i + 1 >= p.N) pf[i].y = 0.0f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) l_tile2 = __fadd2_rn(l_tile2, pf[i]);
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const int phys = (((cc & 63) >> 3) + 2 * hh + ch) ^ (r & 7);
+            uint4 o;
+            o.x = pack2(pf[4 * ch + 0].x, pf[4 * ch + 0].y, is_bf16);
+            o.y = pack2(pf[4 * ch + 1].x, pf[4 * ch + 1].y, is_bf16);
+            o.z = pack2(pf[4 * ch + 2].x, pf[4 * ch + 2].y, is_bf16);
+            o.w = pack2(pf[4 * ch + 3].x, pf[4 * ch + 3].y, is_bf16);
+            *reinterpret_cast<uint4*>(chunk_base + phys * 16) = o;
+          }
         }
       }
       l_run2 = __ffma2_rn(l_run2, make_float2(alpha, alpha), l_tile2);
@@ -305,8 +311,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       mbar_arrive(p_ready);
       // ---- fold O_{j-1} (scaled by the alpha of step j-1) while the tensor core works on S_{j+1}, P_j V_j
       if (j > 0) {
-        tc_fence_after();
-        fold_o(tmem_O + lane_addr + ((j - 1) & 1) * ATT_D, o_acc, alpha_prev);
+        const float2 a2 = make_float2(alpha_prev, alpha_prev);
+        tmem_ld_wait_dep(vbuf[0]);
+        tmem_ld32(o_prev_addr + 32, vbuf[1]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          o_acc[i] = __ffma2_rn(o_acc[i], a2, make_float2(__uint_as_float(vbuf[0][2 * i]), __uint_as_float(vbuf[0][2 * i + 1])));
+        tmem_ld_wait_dep(vbuf[1]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          o_acc[16 + i] = __ffma2_rn(o_acc[16 + i], a2, make_float2(__uint_as_float(vbuf[1][2 * i]), __uint_as_float(vbuf[1][2 * i + 1])));
       }
       alpha_prev = alpha;
     }

@@ -159,35 +159,40 @@ bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
 
 int pick_block_n(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
-template <int BN, int OUT_KIND, int ACT>
+template <int BN, int OUT_KIND, int ACT, bool BF16>
 cudaError_t launch_gemm_inst(const GemmParams& p, int grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<BN, OUT_KIND, ACT><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(p);
+  gemm_tc_kernel<BN, OUT_KIND, ACT, BF16><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(p);
   return cudaGetLastError();
 }
 
-template <int BN>
+template <int BN, bool BF16>
 cudaError_t launch_gemm_bn(const GemmParams& p, int grid, cudaStream_t s) {
-  if (p.out_kind == OUT_F32) return launch_gemm_inst<BN, OUT_F32, ACT_NONE>(p, grid, s);
-  if (p.act == ACT_GELU) return launch_gemm_inst<BN, OUT_HALF, ACT_GELU>(p, grid, s);
-  if (p.act == ACT_RELU) return launch_gemm_inst<BN, OUT_HALF, ACT_RELU>(p, grid, s);
-  return launch_gemm_inst<BN, OUT_HALF, ACT_NONE>(p, grid, s);
+  if (p.out_kind == OUT_F32) return launch_gemm_inst<BN, OUT_F32, ACT_NONE, BF16>(p, grid, s);
+  if (p.act == ACT_GELU) return launch_gemm_inst<BN, OUT_HALF, ACT_GELU, BF16>(p, grid, s);
+  if (p.act == ACT_RELU) return launch_gemm_inst<BN, OUT_HALF, ACT_RELU, BF16>(p, grid, s);
+  return launch_gemm_inst<BN, OUT_HALF, ACT_NONE, BF16>(p, grid, s);
+}
+
+template <bool BF16>
+cudaError_t launch_gemm_dt(const GemmParams& p, int bn, int grid, cudaStream_t s) {
+  if (p.out_kind == OUT_HEAD) return launch_gemm_inst<32, OUT_HEAD, ACT_NONE, BF16>(p, grid, s);
+  switch (bn) {
+    case 32: return launch_gemm_bn<32, BF16>(p, grid, s);
+    case 64: return launch_gemm_bn<64, BF16>(p, grid, s);
+    case 128: return launch_gemm_bn<128, BF16>(p, grid, s);
+    default: return launch_gemm_bn<256, BF16>(p, grid, s);
+  }
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, cudaStream_t s) {
-  if (p.out_kind == OUT_HEAD) return launch_gemm_inst<32, OUT_HEAD, ACT_NONE>(p, grid, s);
-  switch (bn) {
-    case 32: return launch_gemm_bn<32>(p, grid, s);
-    case 64: return launch_gemm_bn<64>(p, grid, s);
-    case 128: return launch_gemm_bn<128>(p, grid, s);
-    default: return launch_gemm_bn<256>(p, grid, s);
-  }
+  return p.is_bf16 ? launch_gemm_dt<true>(p, bn, grid, s) : launch_gemm_dt<false>(p, bn, grid, s);
 }
 
 // Description of one spatial GEMM (see gemm_tc.cuh).
@@ -296,17 +301,21 @@ bool add_gemm(Ctx& c, GemmOp op) {
   return true;
 }
 
-template <bool HAS_BIAS>
-cudaError_t launch_attn(const AttnParams& p, dim3 grid, cudaStream_t s) {
+template <bool HAS_BIAS, bool BF16>
+cudaError_t launch_attn_inst(const AttnParams& p, dim3 grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<HAS_BIAS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ATT_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  attn_tc_kernel<HAS_BIAS><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
+  attn_tc_kernel<HAS_BIAS, BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
   return cudaGetLastError();
+}
+template <bool HAS_BIAS>
+cudaError_t launch_attn(const AttnParams& p, dim3 grid, cudaStream_t s) {
+  return p.is_bf16 ? launch_attn_inst<HAS_BIAS, true>(p, grid, s) : launch_attn_inst<HAS_BIAS, false>(p, grid, s);
 }
 
 // bias (optional): [heads, N, ldb] 16-bit with ldb a multiple of 128
@@ -367,8 +376,8 @@ bool add_resize(Ctx& c, const void* in, void* out, int B, int IH, int IW, int OH
   const int is_bf16 = c.is_bf16;
   const int nsm = c.num_sms;
   c.add("resize:" + c.scope, 0.0, ((double)B * IH * IW + (double)B * OH * OW) * C * 2.0, [=](cudaStream_t s) {
-    const long long total = (long long)B * OH * OW * (C / 8);
-    const int grid = ew_grid(total, 256, nsm);
+    (void)nsm;
+    const dim3 grid((unsigned)((OW * (C / 8) + 255) / 256), (unsigned)OH, (unsigned)B);
     DISPATCH_T(is_bf16, (resize_bilinear_ac_kernel<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, B, IH, IW, OH, OW, C)));
     return cudaGetLastError();
   });

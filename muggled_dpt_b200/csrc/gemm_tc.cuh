@@ -86,16 +86,29 @@ DPT_DEVICE float gelu_erf(float x) {
   p = p * p;
   p = p * p;
   p = p * p;
-  const float e = 1.0f - __frcp_rn(p);  // erf(|x|/sqrt2)
+  const float e = 1.0f - rcp_approx(p);  // erf(|x|/sqrt2)
   const float half_x = 0.5f * x;
   return fmaf(copysignf(e, x), half_x, half_x);
 }
 
-DPT_DEVICE float apply_act(float v, int act) {
-  if (act == ACT_GELU) return gelu_erf(v);
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-v));
-  return v;
+// two GELUs at once with packed fp32x2 FMA (sm_100 FFMA2): same formula as gelu_erf
+DPT_DEVICE float2 gelu_erf2(float2 x) {
+  const float2 z = make_float2(fabsf(x.x) * 0.70710678118654752f, fabsf(x.y) * 0.70710678118654752f);
+  float2 p = __ffma2_rn(z, make_float2(0.0000430638f, 0.0000430638f), make_float2(0.0002765672f, 0.0002765672f));
+  p = __ffma2_rn(z, p, make_float2(0.0001520143f, 0.0001520143f));
+  p = __ffma2_rn(z, p, make_float2(0.0092705272f, 0.0092705272f));
+  p = __ffma2_rn(z, p, make_float2(0.0422820123f, 0.0422820123f));
+  p = __ffma2_rn(z, p, make_float2(0.0705230784f, 0.0705230784f));
+  p = __ffma2_rn(z, p, make_float2(1.0f, 1.0f));
+  p = __fmul2_rn(p, p);
+  p = __fmul2_rn(p, p);
+  p = __fmul2_rn(p, p);
+  p = __fmul2_rn(p, p);
+  float2 e;
+  e.x = copysignf(1.0f - rcp_approx(p.x), x.x);
+  e.y = copysignf(1.0f - rcp_approx(p.y), x.y);
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(e, hx, hx);
 }
 
 DPT_DEVICE uint32_t pack2(float a, float b, int is_bf16) {
@@ -111,7 +124,7 @@ DPT_DEVICE float2 unpack2(uint32_t u, int is_bf16) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int BLOCK_N, int OUT_KIND, int ACT>
+template <int BLOCK_N, int OUT_KIND, int ACT, bool BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, BLOCK_N, p.is_bf16 != 0, false, false);
+      const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, BLOCK_N, BF16, false, false);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -232,7 +245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const bool wg_active = (BLOCK_N >= 64) || (wg == 0);
     uint8_t* stg = staging + ew * GEMM_STAGE_BYTES_PER_WARP;
     const int TW = 1 << p.tw_log2, TH = GEMM_BLOCK_M >> p.tw_log2;
-    const int is_bf16 = p.is_bf16;
+    constexpr int is_bf16 = BF16 ? 1 : 0;
     const int r = q * 32 + lane;  // accumulator row (TMEM lane) owned by this thread
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0;
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           float acc = p.head_b;
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc = fmaf(fmaxf(__uint_as_float(v[j]) + bs[j], 0.0f), p.head_w[j], acc);
-          acc = p.head_act == ACT_SIGMOID ? 1.0f / (1.0f + __expf(-acc)) : fmaxf(acc, 0.0f);
+          acc = p.head_act == ACT_SIGMOID ? rcp_approx(1.0f + __expf(-acc)) : fmaxf(acc, 0.0f);
           if (row_ok) {
             if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.ldo] = __float2bfloat16_rn(acc);
             else reinterpret_cast<__half*>(p.out)[pix * p.ldo] = __float2half_rn(acc);
@@ -282,15 +295,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           constexpr int COLS_PER_STG = F32OUT ? 32 : 64;  // staging row = 128 B
           constexpr int ELEMS_PER_CHUNK = F32OUT ? 4 : 8;
           constexpr int NCOLS_HERE = COLS_PER_STG < COLS_PER_WG ? COLS_PER_STG : COLS_PER_WG;
+          constexpr int UNITS = COLS_PER_WG / 32;             // 32-column TMEM loads per tile and warp
+          constexpr int UNITS_PER_STG = NCOLS_HERE / 32;      // 1 (fp32 out) or 2 (16-bit out)
           const int sub = lane & 7;  // 16-byte chunk within a 128-byte row segment (phase 2)
-#pragma unroll 1
-          for (int c0 = 0; c0 < COLS_PER_WG; c0 += COLS_PER_STG) {
-            // ---- phase 1: my row, NCOLS_HERE columns: TMEM -> +bias, activation -> swizzled staging
+          // software pipeline: the TMEM load of unit u+1 is in flight while unit u is processed / stored
+          uint32_t vbuf[2][32];
+          tmem_ld32(t_acc, vbuf[0]);
 #pragma unroll
-            for (int cc = 0; cc < NCOLS_HERE; cc += 32) {
-              uint32_t v[32];
-              tmem_ld32(t_acc + c0 + cc, v);
-              tmem_ld_wait();
+          for (int u = 0; u < UNITS; ++u) {
+            uint32_t(&v)[32] = vbuf[u & 1];
+            tmem_ld_wait_dep(v);
+            if (u + 1 < UNITS) tmem_ld32(t_acc + (u + 1) * 32, vbuf[(u + 1) & 1]);
+            const int c0 = (u / UNITS_PER_STG) * COLS_PER_STG;   // first column of this staging chunk
+            const int cc = (u % UNITS_PER_STG) * 32;             // column offset inside the staging chunk
+            // ---- phase 1: my row, 32 columns: +bias, activation -> swizzled staging
+            {
               const float4* b4 = reinterpret_cast<const float4*>(bs + col_base + c0 + cc);
               float f[32];
 #pragma unroll
@@ -303,7 +322,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               }
               if constexpr (ACT == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                for (int j = 0; j < 32; j += 2) {
+                  const float2 g = gelu_erf2(make_float2(f[j], f[j + 1]));
+                  f[j] = g.x;
+                  f[j + 1] = g.y;
+                }
               } else if constexpr (ACT == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
@@ -328,23 +351,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 }
               }
             }
+            if ((u % UNITS_PER_STG) != UNITS_PER_STG - 1) continue;  // staging chunk not complete yet
             __syncwarp();
             // ---- phase 2: coalesced global IO; 8 lanes cover one 128-byte row segment, 4 rows per pass, all
             //      eight passes' loads issued before the first store (the residual may alias the output)
             const int ncol0 = n_blk * BLOCK_N + col_base + c0;  // first output column of this staging chunk
             const bool col_ok = (sub * ELEMS_PER_CHUNK < NCOLS_HERE) && (ncol0 + sub * ELEMS_PER_CHUNK) < p.N;
             const long long coff = ncol0 + sub * ELEMS_PER_CHUNK;
-            long long rpix[8];
-            bool ok[8];
-            uint4 val[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + (lane >> 3);
-              rpix[i] = __shfl_sync(0xffffffffu, pix, rr);
-              ok[i] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
-              val[i] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((sub ^ (rr & 7)) * 16));
-            }
             if constexpr (F32OUT) {
+              long long rpix[8];
+              bool ok[8];
+              uint4 val[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + (lane >> 3);
+                rpix[i] = __shfl_sync(0xffffffffu, pix, rr);
+                ok[i] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
+                val[i] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((sub ^ (rr & 7)) * 16));
+              }
               if (p.add1 != nullptr) {
                 float4 a[8];
 #pragma unroll
@@ -363,43 +387,57 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               for (int i = 0; i < 8; ++i)
                 if (ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
             } else {
-              if (p.add1 != nullptr || p.add2 != nullptr || p.out2_relu != nullptr) {
-                const uint4 z = make_uint4(0, 0, 0, 0);
-                uint4 a1[8], a2[8];
+              const bool has_extra = p.add1 != nullptr || p.add2 != nullptr || p.out2_relu != nullptr;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  a1[i] = (p.add1 != nullptr && ok[i])
-                              ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add1) +
-                                                                rpix[i] * p.ld_add1 + coff)
-                              : z;
-                  a2[i] = (p.add2 != nullptr && ok[i])
-                              ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add2) +
-                                                                rpix[i] * p.ld_add2 + coff)
-                              : z;
+              for (int hb = 0; hb < 2; ++hb) {  // two batches of four passes (register pressure)
+                long long rpix[4];
+                bool ok[4];
+                uint4 val[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int rr = 16 * hb + 4 * i + (lane >> 3);
+                  rpix[i] = __shfl_sync(0xffffffffu, pix, rr);
+                  ok[i] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
+                  val[i] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((sub ^ (rr & 7)) * 16));
                 }
+                if (has_extra) {
+                  const uint4 z = make_uint4(0, 0, 0, 0);
+                  uint4 a1[4], a2[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  uint32_t* vv = reinterpret_cast<uint32_t*>(&val[i]);
-                  const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&a1[i]);
-                  const uint32_t* x2 = reinterpret_cast<const uint32_t*>(&a2[i]);
-                  uint4 rv;
-                  uint32_t* rr32 = reinterpret_cast<uint32_t*>(&rv);
-#pragma unroll
-                  for (int w = 0; w < 4; ++w) {
-                    float2 fv = unpack2(vv[w], is_bf16);
-                    const float2 g1 = unpack2(x1[w], is_bf16), g2 = unpack2(x2[w], is_bf16);
-                    fv.x += g1.x + g2.x;
-                    fv.y += g1.y + g2.y;
-                    vv[w] = pack2(fv.x, fv.y, is_bf16);
-                    rr32[w] = pack2(fmaxf(fv.x, 0.f), fmaxf(fv.y, 0.f), is_bf16);
+                  for (int i = 0; i < 4; ++i) {
+                    a1[i] = (p.add1 != nullptr && ok[i])
+                                ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add1) +
+                                                                  rpix[i] * p.ld_add1 + coff)
+                                : z;
+                    a2[i] = (p.add2 != nullptr && ok[i])
+                                ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.add2) +
+                                                                  rpix[i] * p.ld_add2 + coff)
+                                : z;
                   }
-                  if (p.out2_relu != nullptr && ok[i])
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2_relu) + rpix[i] * p.ld_out2 + coff) = rv;
-                }
-              }
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
+                  for (int i = 0; i < 4; ++i) {
+                    uint32_t* vv = reinterpret_cast<uint32_t*>(&val[i]);
+                    const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&a1[i]);
+                    const uint32_t* x2 = reinterpret_cast<const uint32_t*>(&a2[i]);
+                    uint4 rv;
+                    uint32_t* rr32 = reinterpret_cast<uint32_t*>(&rv);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                      float2 fv = unpack2(vv[w], is_bf16);
+                      const float2 g1 = unpack2(x1[w], is_bf16), g2 = unpack2(x2[w], is_bf16);
+                      fv.x += g1.x + g2.x;
+                      fv.y += g1.y + g2.y;
+                      vv[w] = pack2(fv.x, fv.y, is_bf16);
+                      rr32[w] = pack2(fmaxf(fv.x, 0.f), fmaxf(fv.y, 0.f), is_bf16);
+                    }
+                    if (p.out2_relu != nullptr && ok[i])
+                      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2_relu) + rpix[i] * p.ld_out2 + coff) = rv;
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
+              }
             }
             __syncwarp();
           }

@@ -14,7 +14,7 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
-template <typename T> struct Vec8 { T v[8]; };  // 16 bytes
+template <typename T> struct __align__(16) Vec8 { T v[8]; };  // 16 bytes
 
 // ---------------------------------------------------------------------------------------------------------------
 // Patch-embed im2col (patch_embed.py:92-97): img [B,3,H,W] -> A [B*gh*gw, kpad], k = c*P*P + ky*P + kx, zero padded.
@@ -190,37 +190,32 @@ __global__ void layernorm_kernel(const TIN* __restrict__ x, const float* __restr
 template <typename T>
 __global__ void resize_bilinear_ac_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int IH, int IW, int OH,
                                           int OW, int C) {
-  const int cv = C / 8;
-  const long long total = (long long)B * OH * OW * cv;
+  // grid = (ceil(OW * C/8 / blockDim), OH, B): one output row per (blockIdx.y, blockIdx.z), 32-bit index math only
+  const int cv = C >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OW * cv) return;
+  const int ox = i / cv, c8 = i - ox * cv;
+  const int oy = blockIdx.y, b = blockIdx.z;
   const float sy = OH > 1 ? (float)(IH - 1) / (float)(OH - 1) : 0.0f;
   const float sx = OW > 1 ? (float)(IW - 1) / (float)(OW - 1) : 0.0f;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv);
-    long long t = idx / cv;
-    const int ox = (int)(t % OW);
-    t /= OW;
-    const int oy = (int)(t % OH);
-    const int b = (int)(t / OH);
-    const float fy = sy * oy, fx = sx * ox;
-    const int y0 = min((int)fy, IH - 1), x0 = min((int)fx, IW - 1);
-    const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
-    const float ly = fy - y0, lx = fx - x0;
-    const float hy = 1.0f - ly, hx = 1.0f - lx;
-    const T* base = in + (long long)b * IH * IW * C + c8 * 8;
-    const Vec8<T> v00 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y0 * IW + x0) * C);
-    const Vec8<T> v01 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y0 * IW + x1) * C);
-    const Vec8<T> v10 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y1 * IW + x0) * C);
-    const Vec8<T> v11 = *reinterpret_cast<const Vec8<T>*>(base + ((long long)y1 * IW + x1) * C);
-    Vec8<T> o;
+  const float fy = sy * oy, fx = sx * ox;
+  const int y0 = min((int)fy, IH - 1), x0 = min((int)fx, IW - 1);
+  const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float hy = 1.0f - ly, hx = 1.0f - lx;
+  const T* base = in + (size_t)b * IH * IW * C + c8 * 8;
+  const Vec8<T> v00 = *reinterpret_cast<const Vec8<T>*>(base + ((size_t)y0 * IW + x0) * C);
+  const Vec8<T> v01 = *reinterpret_cast<const Vec8<T>*>(base + ((size_t)y0 * IW + x1) * C);
+  const Vec8<T> v10 = *reinterpret_cast<const Vec8<T>*>(base + ((size_t)y1 * IW + x0) * C);
+  const Vec8<T> v11 = *reinterpret_cast<const Vec8<T>*>(base + ((size_t)y1 * IW + x1) * C);
+  Vec8<T> o;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float r = hy * (hx * to_f32(v00.v[i]) + lx * to_f32(v01.v[i])) +
-                      ly * (hx * to_f32(v10.v[i]) + lx * to_f32(v11.v[i]));
-      o.v[i] = from_f32<T>(r);
-    }
-    *reinterpret_cast<Vec8<T>*>(out + (((long long)b * OH + oy) * OW + ox) * C + c8 * 8) = o;
+  for (int k = 0; k < 8; ++k) {
+    const float r = hy * (hx * to_f32(v00.v[k]) + lx * to_f32(v01.v[k])) +
+                    ly * (hx * to_f32(v10.v[k]) + lx * to_f32(v11.v[k]));
+    o.v[k] = from_f32<T>(r);
   }
+  *reinterpret_cast<Vec8<T>*>(out + (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8) = o;
 }
 
 // out = relu(in), 8 elements per thread
