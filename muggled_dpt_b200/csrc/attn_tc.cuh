@@ -7,12 +7,18 @@
 // rows past N are zero-filled by TMA and masked to -inf before the softmax.
 //
 // One CTA = one 128-row query tile of one (batch, head); two CTAs are co-resident per SM so one CTA's tensor-core work
-// overlaps the other's softmax. Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 softmax
-// (one query row per thread).
+// overlaps the other's softmax. Warp roles: warps 0..3 softmax (one query row per thread, 208 registers after
+// setmaxnreg), warp 4 TMA producer, warp 5 MMA issuer (+TMEM alloc).
 //   S = Q K_j^T        tcgen05.mma M=128 N=128 K=64  -> TMEM cols [0,128)
-//   P = exp2(S*c - m)  two passes over S in TMEM (row max, then exp/sum), P written 16-bit to swizzled smem
-//   O_j = P V_j        tcgen05.mma M=128 N=64 K=128 (V is the MN-major B operand, straight from the TMA tile)
-//                      -> TMEM cols [128 + 64*(j&1), +64); accumulated in registers as O = O*alpha_j + O_j.
+//   softmax thread     reads its whole S row (128 fp32) into registers in ONE TMEM pass and releases S at once
+//                      (S_{j+1} is computed while P_j is still being exponentiated); exact row max; the stabiliser mu
+//                      only moves when the max grows by more than 2^8 ("lazy rescale"), so P <= 256 and the
+//                      accumulator rarely needs touching; P = exp2(S*c - mu) 16-bit -> swizzled smem
+//   O += P V_j         tcgen05.mma M=128 N=64 K=128 accumulating in TMEM cols [128,192) (V is the MN-major B operand,
+//                      straight from the TMA tile). On the rare rescale a warp multiplies its 32 accumulator rows by
+//                      exp2(mu_old - mu_new) through tcgen05.ld / tcgen05.st before P_j is published.
+// TMEM read traffic per kv step is one S tile (64 KB) - the SM's TMEM read port (64 B/clk) and the MUFU ex2 rate
+// (16/clk) both cost 1024 cycles per step, which is what bounds this kernel at d = 64.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -21,7 +27,7 @@
 
 namespace dpt {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 256;  // warpgroup 0 = softmax (4 warps), warpgroup 1 = TMA producer, MMA issuer, 2 idle
 constexpr int ATT_BM = 128;   // query rows per CTA
 constexpr int ATT_BN = 128;   // kv rows per step
 constexpr int ATT_D = 64;
@@ -57,19 +63,24 @@ DPT_DEVICE void load_bias32(const uint16_t* src, float (&bf)[32], int is_bf16) {
   }
 }
 
-// o_acc = o_acc * alpha + O_tile (64 fp32 columns of this thread's TMEM lane)
-DPT_DEVICE void fold_o(uint32_t o_addr, float2 (&o_acc)[ATT_D / 2], float alpha) {
-  const float2 a2 = make_float2(alpha, alpha);
+// Rare path of the lazy rescale: this thread's accumulator row (64 fp32 TMEM columns) *= beta. Whole warp calls it.
+__device__ __noinline__ void rescale_accumulator(uint32_t o_addr, float beta) {
+  const float2 b2 = make_float2(beta, beta);
 #pragma unroll
   for (int cc = 0; cc < ATT_D; cc += 32) {
-    uint32_t v[32];
-    tmem_ld32(o_addr + cc, v);
-    tmem_ld_wait();
+    uint32_t ov[32];
+    tmem_ld32(o_addr + cc, ov);
+    tmem_ld_wait_dep(ov);
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      o_acc[cc / 2 + i] = __ffma2_rn(o_acc[cc / 2 + i], a2,
-                                     make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
+    for (int i = 0; i < 32; i += 2) {
+      const float2 t = __fmul2_rn(make_float2(__uint_as_float(ov[i]), __uint_as_float(ov[i + 1])), b2);
+      ov[i] = __float_as_uint(t.x);
+      ov[i + 1] = __float_as_uint(t.y);
+    }
+    tmem_st32(o_addr + cc, ov);
   }
+  tmem_st_wait();
+  tc_fence_before();
 }
 
 template <bool HAS_BIAS, bool BF16>
@@ -88,7 +99,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   uint64_t* s_full = bars + 9;
   uint64_t* p_ready = bars + 10;
   uint64_t* o_full = bars + 11;   // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* s_free = bars + 13;   // S_j has been read out of TMEM for the last time (S_{j+1} may overwrite it)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,9 +125,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     }
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
+    mbar_init(s_free, 128);
     fence_barrier_init();
   }
-  if (warp_idx == 1) {
+  if (warp_idx == 5) {
     tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -124,9 +137,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 128;  // single fp32 accumulator [128 x 64]
 
-  if (warp_idx == 0) {
+  // Register rebalancing (setmaxnreg is per warpgroup): the kernel launches at 128 registers/thread so that two CTAs
+  // fit an SM; the producer/MMA warpgroup gives most of its registers back and the softmax warpgroup, which keeps a
+  // whole 128-column S row per thread, takes them.
+  if (warp_idx >= 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp_idx == 4) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
@@ -143,7 +161,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       }
     }
     __syncwarp();
-  } else if (warp_idx == 1) {
+  } else if (warp_idx == 5) {
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_f16(128, ATT_BN, BF16, false, false);
@@ -165,12 +183,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        // P_j is in smem and S_j has been fully read out of TMEM
-        mbar_wait(p_ready, j & 1);
-        tc_fence_after();
+        // S_{j+1} as soon as S_j has been read for the last time (the softmax warps are still exponentiating)
         if (j + 1 < n_kv) {
           const int s1 = (j + 1) & 1;
           const uint32_t ph1 = ((j + 1) >> 1) & 1;
+          mbar_wait(s_free, j & 1);
           mbar_wait(&k_full[s1], ph1);
           tc_fence_after();
           const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK + s1 * ATT_TILE_BYTES));
@@ -179,22 +196,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
           umma_commit(&k_empty[s1]);
           umma_commit(s_full);
         }
+        // P_j is in smem
+        mbar_wait(p_ready, j & 1);
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
         const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV + s * ATT_TILE_BYTES));
-        const uint32_t d_o = tmem_O + (j & 1) * ATT_D;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t a_desc = (kk < 4 ? p_desc0 : p_desc1) + 2 * (kk & 3);
           // V rows kk*16.. : 16 rows * 128 B = 2048 B -> +128 in the (addr >> 4) field
-          umma_f16_ss(d_o, a_desc, v_desc + 128 * kk, idesc_o, kk != 0);
+          umma_f16_ss(tmem_O, a_desc, v_desc + 128 * kk, idesc_o, (j | kk) != 0);
         }
         umma_commit(&v_empty[s]);
         umma_commit(&o_full[j & 1]);
       }
     }
     __syncwarp();
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ===================================== softmax / output =====================================
     const int q = warp_idx & 3;          // TMEM lane quarter
     const int r = q * 32 + lane;         // query row within the tile
@@ -202,153 +222,145 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     constexpr int is_bf16 = BF16 ? 1 : 0;
     const float c = p.scale_log2;
     const float2 c2 = make_float2(c, c);
-    float m_run = -INFINITY;   // running max, in exp2 units (score * scale * log2e [+ bias * log2e])
-    float2 l_run2 = make_float2(0.0f, 0.0f);
-    float alpha_prev = 1.0f;
-    float2 o_acc[ATT_D / 2];
+    float mu = -INFINITY;  // stabiliser in exp2 units (score * scale * log2e [+ bias * log2e]); >= row max - 8
+    float2 l2[4];          // row sum of P, four independent packed accumulators
 #pragma unroll
-    for (int i = 0; i < ATT_D / 2; ++i) o_acc[i] = make_float2(0.0f, 0.0f);
+    for (int i = 0; i < 4; ++i) l2[i] = make_float2(0.0f, 0.0f);
     const int qrow = q0 + r;
     const uint16_t* bias_row = nullptr;
     if constexpr (HAS_BIAS) {
-      // rows past N read row N-1 (their results are never stored); ldb is a multiple of ATT_BN so whole tiles are
-      // in bounds
+      // rows past N read row N-1 (never stored); ldb is a multiple of ATT_BN so whole kv tiles are in bounds
       bias_row = reinterpret_cast<const uint16_t*>(p.bias) + ((long long)h * p.N + min(qrow, p.N - 1)) * p.ldb;
     }
+    const uint32_t s_addr = tmem_S + lane_addr;
+    const uint32_t o_addr = tmem_O + lane_addr;
 
-    uint32_t vbuf[2][32];  // software-pipelined TMEM reads: chunk i+1 is in flight while chunk i is processed
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv0 = j * ATT_BN;
       const bool tail = (kv0 + ATT_BN > p.N);
-      const uint32_t s_addr = tmem_S + lane_addr;
-      // ---- pass 1: row max
-      float m_tile = -INFINITY;
-      tmem_ld32(s_addr, vbuf[0]);
+      // ---- the whole S row -> registers, then S is free for the next QK^T
+      uint32_t sv[4][32];
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        uint32_t(&v)[32] = vbuf[ci & 1];
-        const int cc = ci * 32;
-        tmem_ld_wait_dep(v);
-        tmem_ld32(s_addr + ((ci + 1) & 3) * 32, vbuf[(ci + 1) & 1]);  // after chunk 3: chunk 0 again, for pass 2
-        if constexpr (HAS_BIAS) {
+      for (int ci = 0; ci < 4; ++ci) tmem_ld32(s_addr + ci * 32, sv[ci]);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) tmem_ld_wait_dep(sv[ci]);
+      tc_fence_before();
+      mbar_arrive(s_free);
+      if constexpr (HAS_BIAS) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
           float bf[32];
-          load_bias32(bias_row + kv0 + cc, bf, is_bf16);
+          load_bias32(bias_row + kv0 + ci * 32, bf, is_bf16);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), c, bf[i]));
+          for (int i = 0; i < 32; ++i) sv[ci][i] = __float_as_uint(fmaf(__uint_as_float(sv[ci][i]), c, bf[i]));
         }
-        if (tail) {
+      }
+      if (tail) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (kv0 + cc + i >= p.N) v[i] = 0xff800000u;  // -inf
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            if (kv0 + ci * 32 + i >= p.N) sv[ci][i] = 0xff800000u;  // -inf
       }
+      // ---- exact row max (four independent chains)
+      float m_t[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            m_t[k] = fmaxf(m_t[k], fmaxf(__uint_as_float(sv[ci][i + 2 * k]), __uint_as_float(sv[ci][i + 2 * k + 1])));
+      float m_tile = fmaxf(fmaxf(m_t[0], m_t[1]), fmaxf(m_t[2], m_t[3]));
       if constexpr (!HAS_BIAS) m_tile *= c;  // max(c*s) = c*max(s), c > 0
-      const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = ex2_approx(m_run - m_new);  // first tile: exp2(-inf) = 0
-      const float2 neg_m2 = make_float2(-m_new, -m_new);
-      // ---- the previous P@V must have consumed the P buffer before it is overwritten
-      if (j > 0) mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-      const uint32_t o_prev_addr = tmem_O + lane_addr + ((j - 1) & 1) * ATT_D;
-      // ---- pass 2: P = exp2(s*c - m_new), row sum, 16-bit P -> swizzled smem
-      float2 l_tile2 = make_float2(0.0f, 0.0f);
+      // ---- lazy rescale decision: move the stabiliser only when the row max outgrew it by more than 2^8
+      const bool need = m_tile > mu + 8.0f;  // always true for j == 0 (mu = -inf)
+      const bool warp_rescale = (j > 0) && __any_sync(0xffffffffu, need);
+      float beta = 1.0f;
+      if (j == 0) {
+        mu = m_tile;
+      } else if (warp_rescale) {
+        const float mu_new = need ? m_tile : mu;
+        beta = ex2_approx(mu - mu_new);  // 1 for rows that keep their stabiliser
+        mu = mu_new;
+        const float2 b2 = make_float2(beta, beta);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l2[i] = __fmul2_rn(l2[i], b2);
+      }
+      // ---- P = exp2(s*c - mu) (<= 256) and the row sum, kept packed in registers while P_{j-1} V_{j-1} finishes
+      const float2 neg_mu2 = make_float2(-mu, -mu);
+      uint32_t pk[64];
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
-        uint32_t(&v)[32] = vbuf[ci & 1];
-        const int cc = ci * 32;
-        tmem_ld_wait_dep(v);
-        if (ci + 1 < 4) tmem_ld32(s_addr + (ci + 1) * 32, vbuf[(ci + 1) & 1]);
-        else if (j > 0) tmem_ld32(o_prev_addr, vbuf[0]);  // first half of O_{j-1}, folded after the arrive below
-        float bf[HAS_BIAS ? 32 : 1];
-        if constexpr (HAS_BIAS) load_bias32(bias_row + kv0 + cc, *reinterpret_cast<float(*)[32]>(&bf), is_bf16);
-        uint8_t* chunk_base = sP + (cc >> 6) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {  // 16 columns at a time keeps the live register set small
-          float2 pf[8];
+        for (int g = 0; g < 4; ++g) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 sv = make_float2(__uint_as_float(v[16 * hh + 2 * i]), __uint_as_float(v[16 * hh + 2 * i + 1]));
-            if constexpr (HAS_BIAS)
-              pf[i] = __fadd2_rn(__ffma2_rn(sv, c2, make_float2(bf[16 * hh + 2 * i], bf[16 * hh + 2 * i + 1])), neg_m2);
-            else
-              pf[i] = __ffma2_rn(sv, c2, neg_m2);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            pf[i].x = ex2_approx(pf[i].x);
-            pf[i].y = ex2_approx(pf[i].y);
-          }
-          if (tail) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (kv0 + cc + 16 * hh + 2 * i >= p.N) pf[i].x = 0.0f;
-              if (kv0 + cc + 16 * hh + 2 * i + 1 >= p.N) pf[i].y = 0.0f;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) l_tile2 = __fadd2_rn(l_tile2, pf[i]);
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            const int phys = (((cc & 63) >> 3) + 2 * hh + ch) ^ (r & 7);
-            uint4 o;
-            o.x = pack2(pf[4 * ch + 0].x, pf[4 * ch + 0].y, is_bf16);
-            o.y = pack2(pf[4 * ch + 1].x, pf[4 * ch + 1].y, is_bf16);
-            o.z = pack2(pf[4 * ch + 2].x, pf[4 * ch + 2].y, is_bf16);
-            o.w = pack2(pf[4 * ch + 3].x, pf[4 * ch + 3].y, is_bf16);
-            *reinterpret_cast<uint4*>(chunk_base + phys * 16) = o;
+          for (int i = 0; i < 4; ++i) {
+            const float2 x = make_float2(__uint_as_float(sv[ci][8 * g + 2 * i]), __uint_as_float(sv[ci][8 * g + 2 * i + 1]));
+            float2 pf;
+            if constexpr (HAS_BIAS) pf = __fadd2_rn(x, neg_mu2);  // bias and scale already applied
+            else pf = __ffma2_rn(x, c2, neg_mu2);
+            pf.x = ex2_approx(pf.x);  // ex2(-inf) = 0 for the masked tail
+            pf.y = ex2_approx(pf.y);
+            l2[i] = __fadd2_rn(l2[i], pf);
+            pk[ci * 16 + g * 4 + i] = pack2(pf.x, pf.y, is_bf16);
           }
         }
       }
-      l_run2 = __ffma2_rn(l_run2, make_float2(alpha, alpha), l_tile2);
-      m_run = m_new;
-      // make P visible to the tensor core (async proxy) and release S
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      // ---- fold O_{j-1} (scaled by the alpha of step j-1) while the tensor core works on S_{j+1}, P_j V_j
+      // ---- the previous P@V must be complete: it reads the P buffer and writes the accumulator
       if (j > 0) {
-        const float2 a2 = make_float2(alpha_prev, alpha_prev);
-        tmem_ld_wait_dep(vbuf[0]);
-        tmem_ld32(o_prev_addr + 32, vbuf[1]);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          o_acc[i] = __ffma2_rn(o_acc[i], a2, make_float2(__uint_as_float(vbuf[0][2 * i]), __uint_as_float(vbuf[0][2 * i + 1])));
-        tmem_ld_wait_dep(vbuf[1]);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          o_acc[16 + i] = __ffma2_rn(o_acc[16 + i], a2, make_float2(__uint_as_float(vbuf[1][2 * i]), __uint_as_float(vbuf[1][2 * i + 1])));
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        if (warp_rescale) rescale_accumulator(o_addr, beta);  // out of line: rare
       }
-      alpha_prev = alpha;
+      // ---- 16-bit P -> swizzled smem
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        uint8_t* chunk_base = sP + (ci >> 1) * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte smem chunk
+          const int phys = (((ci & 1) * 4) + g) ^ (r & 7);
+          *reinterpret_cast<uint4*>(chunk_base + phys * 16) =
+              make_uint4(pk[ci * 16 + g * 4 + 0], pk[ci * 16 + g * 4 + 1], pk[ci * 16 + g * 4 + 2], pk[ci * 16 + g * 4 + 3]);
+        }
+      }
+      // make P visible to the tensor core (async proxy); P_j V_j is issued after this
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
     }
-    // last O tile
+    // ---- epilogue: O / l
     {
       const int j = n_kv - 1;
       mbar_wait(&o_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      fold_o(tmem_O + lane_addr + (j & 1) * ATT_D, o_acc, alpha_prev);
-    }
-    if (qrow < p.N) {
-      const float inv_l = 1.0f / (l_run2.x + l_run2.y);
-      uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)b * p.N + qrow) * p.F + h * ATT_D;
+      const float2 ls = __fadd2_rn(__fadd2_rn(l2[0], l2[1]), __fadd2_rn(l2[2], l2[3]));
+      const float inv_l = 1.0f / (ls.x + ls.y);
+      uint32_t ov[2][32];
+      tmem_ld32(o_addr, ov[0]);
+      tmem_ld32(o_addr + 32, ov[1]);
+      tmem_ld_wait_dep(ov[0]);
+      tmem_ld_wait_dep(ov[1]);
+      if (qrow < p.N) {
+        uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)b * p.N + qrow) * p.F + h * ATT_D;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 o;
-        o.x = pack2(o_acc[4 * ch + 0].x * inv_l, o_acc[4 * ch + 0].y * inv_l, is_bf16);
-        o.y = pack2(o_acc[4 * ch + 1].x * inv_l, o_acc[4 * ch + 1].y * inv_l, is_bf16);
-        o.z = pack2(o_acc[4 * ch + 2].x * inv_l, o_acc[4 * ch + 2].y * inv_l, is_bf16);
-        o.w = pack2(o_acc[4 * ch + 3].x * inv_l, o_acc[4 * ch + 3].y * inv_l, is_bf16);
-        *reinterpret_cast<uint4*>(orow + 8 * ch) = o;
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t* w = &ov[ch >> 2][(ch & 3) * 8];
+          uint4 o;
+          o.x = pack2(__uint_as_float(w[0]) * inv_l, __uint_as_float(w[1]) * inv_l, is_bf16);
+          o.y = pack2(__uint_as_float(w[2]) * inv_l, __uint_as_float(w[3]) * inv_l, is_bf16);
+          o.z = pack2(__uint_as_float(w[4]) * inv_l, __uint_as_float(w[5]) * inv_l, is_bf16);
+          o.w = pack2(__uint_as_float(w[6]) * inv_l, __uint_as_float(w[7]) * inv_l, is_bf16);
+          *reinterpret_cast<uint4*>(orow + 8 * ch) = o;
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 1) {
+  if (warp_idx == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }

@@ -57,19 +57,15 @@ DPT_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Slow path, kept out of line: a broken pipeline traps (-> launch failure reported to the host) instead of hanging.
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a broken pipeline traps (-> launch failure reported to the host) instead of hanging the GPU.
+// Kept inline (no call): an out-of-line callee shared by warpgroups running under different setmaxnreg budgets
+// defeats ptxas' per-region register allocation.
+DPT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s
-      printf("dpt: mbarrier wait timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
-             (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s
   }
-}
-DPT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // named barrier among a subset of the CTA's warps
@@ -161,6 +157,19 @@ DPT_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 DPT_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: thread t of the warp writes lane (32*(warp%4) + t), 32 consecutive 32-bit columns
+DPT_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+DPT_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Same, but makes the loaded registers depend on the wait so the compiler cannot hoist their uses above it when the
 // load was issued earlier (software-pipelined TMEM reads).
 DPT_DEVICE void tmem_ld_wait_dep(uint32_t (&v)[32]) {
