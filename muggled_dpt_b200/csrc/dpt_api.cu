@@ -204,6 +204,7 @@ struct GemmOp {
   const void* Wt_ptr = nullptr;       // [N, taps*kpad] 16-bit
   int N = 0, taps = 1, kpad = 0;
   const float* bias = nullptr;
+  long long bias_bstride = 0;         // per-image bias vectors (BEiT readout)
   int act = ACT_NONE;
   int out_kind = OUT_HALF;
   void* out = nullptr;
@@ -272,6 +273,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
   p.a_xoff = op.xoff;
   p.is_bf16 = c.is_bf16;
   p.bias = op.bias;
+  p.bias_bstride = op.bias_bstride;
   p.act = op.act;
   p.out_kind = op.out_kind;
   p.out = op.out;
@@ -468,25 +470,45 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
   void* att = c.ar.alloc((size_t)M * F * 2);
   void* hid = c.ar.alloc((size_t)M * 4 * F * 2);
 
-  const Weight* base = get_w(c, "pos.base", DPT_F32);
-  const Weight* cls_tok = get_w(c, "pos.cls_tok", DPT_F32);
-  const Weight* cls_emb = get_w(c, "pos.cls_emb", DPT_F32);
-  const Weight* on_w = get_w(c, "outnorm.w", DPT_F32);
-  const Weight* on_b = get_w(c, "outnorm.b", DPT_F32);
-  if (!base || !cls_tok || !cls_emb || !on_w || !on_b) return false;
-  if (!c.dry) {
-    const int bh = cfg.base_grid_h, bw = cfg.base_grid_w;
-    const int is_bf16 = c.is_bf16, nsm = c.num_sms;
-    const float *bp = (const float*)base->ptr, *ct = (const float*)cls_tok->ptr, *ce = (const float*)cls_emb->ptr;
-    c.add("pos_table", 0.0, (double)N * F * 4.0, [=](cudaStream_t s) {
-      pos_table_kernel<<<N, 128, 0, s>>>(bp, ct, ce, pos, bh, bw, gh, gw, F);
-      return cudaGetLastError();
-    });
-    c.add("assemble_tokens", 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
-      const int grid = ew_grid(M * F / 4, 256, nsm);
-      DISPATCH_T(is_bf16, (assemble_tokens_kernel<T><<<grid, 256, 0, s>>>((const T*)tokens, pos, x, B, N, F)));
-      return cudaGetLastError();
-    });
+  const bool is_beit = cfg.variant == DPT_VARIANT_BEIT;
+  const Weight *on_w = nullptr, *on_b = nullptr;
+  void* bias_buf = nullptr;
+  const long long ldb = (N + ATT_BN - 1) / ATT_BN * ATT_BN;
+  if (!is_beit) {
+    const Weight* base = get_w(c, "pos.base", DPT_F32);
+    const Weight* cls_tok = get_w(c, "pos.cls_tok", DPT_F32);
+    const Weight* cls_emb = get_w(c, "pos.cls_emb", DPT_F32);
+    on_w = get_w(c, "outnorm.w", DPT_F32);
+    on_b = get_w(c, "outnorm.b", DPT_F32);
+    if (!base || !cls_tok || !cls_emb || !on_w || !on_b) return false;
+    if (!c.dry) {
+      const int bh = cfg.base_grid_h, bw = cfg.base_grid_w;
+      const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+      const float *bp = (const float*)base->ptr, *ct = (const float*)cls_tok->ptr, *ce = (const float*)cls_emb->ptr;
+      c.add("pos_table", 0.0, (double)N * F * 4.0, [=](cudaStream_t s) {
+        pos_table_kernel<<<N, 128, 0, s>>>(bp, ct, ce, pos, bh, bw, gh, gw, F);
+        return cudaGetLastError();
+      });
+      c.add("assemble_tokens", 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
+        const int grid = ew_grid(M * F / 4, 256, nsm);
+        DISPATCH_T(is_bf16, (assemble_tokens_kernel<T><<<grid, 256, 0, s>>>((const T*)tokens, pos, x, B, N, F, N)));
+        return cudaGetLastError();
+      });
+    }
+  } else {
+    // BEiT: cls token only, no position embedding (v31_beit/image_encoder_model.py:77-79); per-layer bias tables
+    const Weight* cls = get_w(c, "beit.cls", DPT_F32);
+    if (!cls) return false;
+    bias_buf = c.ar.alloc((size_t)heads * N * ldb * 2);
+    if (!c.dry) {
+      const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+      const float* cp = (const float*)cls->ptr;
+      c.add("assemble_tokens", 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
+        const int grid = ew_grid(M * F / 4, 256, nsm);
+        DISPATCH_T(is_bf16, (assemble_tokens_kernel<T><<<grid, 256, 0, s>>>((const T*)tokens, cp, x, B, N, F, 1)));
+        return cudaGetLastError();
+      });
+    }
   }
   const float scale = 1.0f / sqrtf(64.0f);
   for (int i = 0; i < L && c.ok; ++i) {
@@ -507,7 +529,25 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       op.bias = (const float*)qb->ptr; op.out = qkv; op.label = "qkv";
       add_gemm(c, op);
     }
-    add_attention(c, qkv, nullptr, 0, att, B, N, heads, scale);
+    if (is_beit) {
+      // relative position bias of this layer -> [H, N, ldb] (relative_positional_encoder.py:242-309)
+      const Weight* tb = get_w(c, pre + "relpos.table", DPT_F32);
+      if (!tb) return false;
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16;
+        const int bh = cfg.base_grid_h, bw = cfg.base_grid_w;
+        const float* tp = (const float*)tb->ptr;
+        void* bb = bias_buf;
+        const int ldbi = (int)ldb;
+        c.add("beit_bias_table:" + pre, 0.0, (double)heads * N * ldb * 2.0, [=](cudaStream_t s) {
+          DISPATCH_T(is_bf16, (beit_bias_table_kernel<T><<<dim3(N, heads), 128, 0, s>>>(tp, (T*)bb, heads, bh, bw, gh, gw, ldbi)));
+          return cudaGetLastError();
+        });
+      }
+      add_attention(c, qkv, bias_buf, ldb, att, B, N, heads, scale);
+    } else {
+      add_attention(c, qkv, nullptr, 0, att, B, N, heads, scale);
+    }
     {
       GemmOp op;  // x += (gamma1 . proj)(att)   (LayerScale folded into the packed weights)
       op.A = att; op.Wt = (int)M; op.C = F; op.Wt_ptr = pw->ptr; op.N = F; op.kpad = (int)pw->shape[1];
@@ -530,7 +570,17 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     if ((i + 1) % per_stage == 0) {
       const int st = (i + 1) / per_stage - 1;
       c.scope = "outnorm" + std::to_string(st);
-      add_layernorm(c, x, (const float*)on_w->ptr, (const float*)on_b->ptr, taps[st], M, F, cfg.ln_eps);
+      if (!is_beit) {
+        add_layernorm(c, x, (const float*)on_w->ptr, (const float*)on_b->ptr, taps[st], M, F, cfg.ln_eps);
+      } else if (!c.dry) {  // BEiT taps are the raw residual stream
+        const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+        void* tp = taps[st];
+        c.add("cast_tap:" + c.scope, 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
+          const int grid = ew_grid(M * F / 4, 256, nsm);
+          DISPATCH_T(is_bf16, (cast_f32_kernel<T><<<grid, 256, 0, s>>>(x, (T*)tp, M * F / 4)));
+          return cudaGetLastError();
+        });
+      }
     }
   }
   c.ar.reset(mk);
@@ -555,9 +605,39 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
     if (!c.ok) return false;
     const size_t mk2 = c.ar.mark();
     c.scope = pre;
-    // 1x1 projection on the patch tokens (cls row skipped through the TMA x offset)
     void* proj = c.ar.alloc((size_t)B * gh * gw * R * 2);
-    {
+    if (cfg.variant == DPT_VARIANT_BEIT) {
+      // readout projection: GELU(Linear(2F,F)([patch, cls])) = GELU(W1 patch + (W2 cls + b)), the bracket being one
+      // vector per image (readout_projection.py:71-81)
+      const Weight *w1 = get_w(c, pre + "readout.w1", hd), *w2 = get_w(c, pre + "readout.w2", DPT_F32);
+      const Weight* rb = get_w(c, pre + "readout.b", DPT_F32);
+      if (!c.ok) return false;
+      float* u = (float*)c.ar.alloc((size_t)B * F * 4);
+      void* ro = c.ar.alloc((size_t)B * gh * gw * F * 2);
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16;
+        const void* tp = taps[k];
+        const float *w2p = (const float*)w2->ptr, *rbp = (const float*)rb->ptr;
+        c.add("readout_vec:" + pre, 2.0 * B * F * F, (double)F * F * 4.0, [=](cudaStream_t s) {
+          const int warps = B * F;
+          DISPATCH_T(is_bf16, (readout_vec_kernel<T><<<(warps * 32 + 255) / 256, 256, 0, s>>>((const T*)tp, w2p, rbp, u, B, N, F)));
+          return cudaGetLastError();
+        });
+      }
+      {
+        GemmOp op;
+        op.A = taps[k]; op.B = B; op.Ht = 1; op.Wt = N; op.C = F; op.xoff = 1;
+        op.Wt_ptr = w1->ptr; op.N = F; op.kpad = (int)w1->shape[1];
+        op.bias = u; op.bias_bstride = F; op.act = ACT_GELU; op.out = ro; op.label = "readout";
+        add_gemm(c, op);
+      }
+      GemmOp op;
+      op.A = ro; op.B = 1; op.Ht = 1; op.Wt = B * gh * gw; op.C = F;
+      op.Wt_ptr = pw->ptr; op.N = R; op.kpad = (int)pw->shape[1];
+      op.bias = (const float*)pb->ptr; op.out = proj; op.label = "proj1x1";
+      add_gemm(c, op);
+    } else {
+      // 1x1 projection on the patch tokens (cls row skipped through the TMA x offset)
       GemmOp op;
       op.A = taps[k]; op.B = B; op.Ht = 1; op.Wt = N; op.C = F; op.xoff = 1;
       op.Wt_ptr = pw->ptr; op.N = R; op.kpad = (int)pw->shape[1];
@@ -848,7 +928,10 @@ const char* dpt_version(void) { return "dpt_b200 0.1 (sm_100a)"; }
 
 int dpt_create(const dpt_config* cfg, dpt_handle* out) {
   if (!cfg || !out) { g_err = "null argument"; return DPT_ERR_INVALID; }
-  if (cfg->variant != DPT_VARIANT_DINOV2) { g_err = "variant not supported by this build"; return DPT_ERR_UNSUPPORTED; }
+  if (cfg->variant != DPT_VARIANT_DINOV2 && cfg->variant != DPT_VARIANT_BEIT) {
+    g_err = "variant not supported by this build";
+    return DPT_ERR_UNSUPPORTED;
+  }
   if (cfg->dtype != DPT_BF16 && cfg->dtype != DPT_F16) { g_err = "dtype must be fp16 or bf16"; return DPT_ERR_INVALID; }
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

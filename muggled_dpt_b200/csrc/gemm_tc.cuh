@@ -43,7 +43,8 @@ struct __align__(64) GemmParams {
   int a_xoff;       // added to the x coordinate of every A load (token mode: 1 skips the cls row)
   int is_bf16;      // 16-bit type of A / Wt / 16-bit outputs: 1 = bf16, 0 = fp16
   // epilogue
-  const float* bias;  // [N] or null
+  const float* bias;  // [N] or null; bias_bstride != 0: one bias vector per image b at bias + b * bias_bstride
+  long long bias_bstride;
   int act;
   int out_kind;
   void* out;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       float* bs = bias_s + as * BLOCK_N;
       if (et < BLOCK_N) {
         const int n = n_blk * BLOCK_N + et;
-        bs[et] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+        bs[et] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + (long long)b * p.bias_bstride + n) : 0.0f;
       }
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
 

@@ -108,9 +108,10 @@ __global__ void pos_table_kernel(const float* __restrict__ base, const float* __
 }
 
 // x32[b,0,:] = pos[0,:]; x32[b,1+p,:] = tok[b,p,:] + pos[1+p,:]   (image_encoder_model.py:83-84)
+// pos_rows == N: full table; pos_rows == 1: only the cls row exists (BEiT: no position embedding on patches)
 template <typename T>
 __global__ void assemble_tokens_kernel(const T* __restrict__ tok, const float* __restrict__ pos, float* __restrict__ x,
-                                       int B, int N, int F) {
+                                       int B, int N, int F, int pos_rows) {
   const long long total = (long long)B * N * F / 4;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -119,7 +120,8 @@ __global__ void assemble_tokens_kernel(const T* __restrict__ tok, const float* _
     const long long row = e / F;
     const int n = (int)(row % N);
     const int b = (int)(row / N);
-    float4 pv = *reinterpret_cast<const float4*>(pos + (long long)n * F + f);
+    float4 pv = (n < pos_rows) ? *reinterpret_cast<const float4*>(pos + (long long)n * F + f)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
     if (n > 0) {
       const T* t = tok + ((long long)b * (N - 1) + (n - 1)) * F + f;
       pv.x += to_f32(t[0]); pv.y += to_f32(t[1]); pv.z += to_f32(t[2]); pv.w += to_f32(t[3]);
@@ -228,6 +230,73 @@ __global__ void relu_copy_kernel(const T* __restrict__ in, T* __restrict__ out, 
     for (int i = 0; i < 8; ++i) v.v[i] = from_f32<T>(fmaxf(to_f32(v.v[i]), 0.0f));
     reinterpret_cast<Vec8<T>*>(out)[idx] = v;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 -> 16-bit cast (BEiT taps: the encoder has no output norm), 4 elements per thread
+template <typename T>
+__global__ void cast_f32_kernel(const float* __restrict__ in, T* __restrict__ out, long long n4) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n4;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[idx];
+    T o[4] = {from_f32<T>(v.x), from_f32<T>(v.y), from_f32<T>(v.z), from_f32<T>(v.w)};
+    reinterpret_cast<uint2*>(out)[idx] = *reinterpret_cast<uint2*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BEiT relative position bias (v31_beit/components/relative_positional_encoder.py:117-309):
+// out[h, i, j] = lut'[index(i, j), h], lut' = bilinear resize (align_corners=False) of the reference table
+// [(2bh-1)*(2bw-1) + 3, H] to (2gh-1, 2gw-1), the three extra rows being cls->token, token->cls, cls->cls.
+// out is [H, N, ldb] 16-bit, columns >= N zero. One block per (i, h).
+template <typename T>
+__global__ void beit_bias_table_kernel(const float* __restrict__ table, T* __restrict__ out, int heads, int bh, int bw,
+                                       int gh, int gw, int ldb) {
+  const int i = blockIdx.x, h = blockIdx.y;
+  const int N = gh * gw + 1;
+  const int rh = 2 * bh - 1, rw = 2 * bw - 1, nh = 2 * gh - 1, nw = 2 * gw - 1;
+  const float* cls_rows = table + (long long)rh * rw * heads;
+  const float sy = (float)rh / (float)nh, sx = (float)rw / (float)nw;
+  T* orow = out + ((long long)h * N + i) * ldb;
+  const int yi = (i - 1) / gw, xi = (i - 1) % gw;
+  for (int j = threadIdx.x; j < ldb; j += blockDim.x) {
+    float v = 0.0f;
+    if (j < N) {
+      if (i == 0 && j == 0) v = cls_rows[2 * heads + h];
+      else if (i == 0) v = cls_rows[0 * heads + h];
+      else if (j == 0) v = cls_rows[1 * heads + h];
+      else {
+        const int yj = (j - 1) / gw, xj = (j - 1) % gw;
+        const int ry = yi - yj + gh - 1, rx = xi - xj + gw - 1;  // position in the resized (nh x nw) table
+        const float fy = fmaxf(sy * (ry + 0.5f) - 0.5f, 0.0f), fx = fmaxf(sx * (rx + 0.5f) - 0.5f, 0.0f);
+        const int y0 = min((int)fy, rh - 1), x0 = min((int)fx, rw - 1);
+        const int y1 = min(y0 + 1, rh - 1), x1 = min(x0 + 1, rw - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        const float t00 = table[((long long)y0 * rw + x0) * heads + h], t01 = table[((long long)y0 * rw + x1) * heads + h];
+        const float t10 = table[((long long)y1 * rw + x0) * heads + h], t11 = table[((long long)y1 * rw + x1) * heads + h];
+        v = (1.0f - ly) * ((1.0f - lx) * t00 + lx * t01) + ly * ((1.0f - lx) * t10 + lx * t11);
+      }
+    }
+    orow[j] = from_f32<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BEiT readout (v31_beit/components/readout_projection.py:71-81): the cls half of Linear(2F, F) is constant per image:
+// u[b, n] = bias[n] + sum_k W2[n, k] * cls[b, k], cls = tap[b, 0, :]. One warp per output.
+template <typename T>
+__global__ void readout_vec_kernel(const T* __restrict__ tap, const float* __restrict__ w2, const float* __restrict__ bias,
+                                   float* __restrict__ u, int B, int N, int F) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * F) return;
+  const int b = warp / F, n = warp % F;
+  const T* cls = tap + (long long)b * N * F;
+  const float* wr = w2 + (long long)n * F;
+  float acc = 0.0f;
+  for (int k = lane; k < F; k += 32) acc = fmaf(wr[k], to_f32(cls[k]), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) u[warp] = acc + bias[n];
 }
 
 }  // namespace dpt

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .weights import pack_depthanything_v2
+from .weights import pack_beit, pack_depthanything_v2
 
 _TORCH_TO_DPT = {torch.float16: N.DPT_F16, torch.bfloat16: N.DPT_BF16}
 
@@ -33,9 +33,19 @@ class _Stage:
 
 
 class _PatchEmbedStage(_Stage):
-    # input normalisation constants - v2_depthanything/patch_embed.py:38-39
-    rgb_offset = (0.485, 0.456, 0.406)
-    rgb_stdev = (0.229, 0.224, 0.225)
+    # input normalisation constants - v2_depthanything/patch_embed.py:38-39 ; v31_beit/patch_embed.py:38-39
+    NORMALISATION = {
+        "depthanythingv2": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
+        "beit": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+    }
+
+    @property
+    def rgb_offset(self):
+        return self.NORMALISATION[self._model.model_type][0]
+
+    @property
+    def rgb_stdev(self):
+        return self.NORMALISATION[self._model.model_type][1]
 
     def prepare_image(self, image_bgr, max_side_length=None, use_square_sizing=True, interpolation_mode="bilinear"):
         """PatchEmbed.prepare_image - v2_depthanything/patch_embed.py:103-145 (host-side glue, outside forward())"""
@@ -76,13 +86,19 @@ class _PatchEmbedStage(_Stage):
 
 
 class DPTModel(torch.nn.Module):
-    def __init__(self, config: dict, state_dict: dict, strict_load: bool = True):
+    def __init__(self, config: dict, state_dict: dict, strict_load: bool = True, model_type: str = "depthanythingv2"):
         super().__init__()
         self.config = dict(config)
+        self.model_type = model_type
         if self.config.get("is_giant", False):
             raise NotImplementedError("ViT-G (SwiGLU) is not built in this round")
+        if self.config["features_per_token"] != 64 * self.config["num_heads"]:
+            raise NotImplementedError("the attention kernel is built for 64 features per head")
         # fp32 CPU copies in kernel layouts; moved/cast by .to()
-        self._packed_cpu = pack_depthanything_v2(state_dict, self.config, strict=strict_load)
+        if model_type == "beit":
+            self._packed_cpu = pack_beit(state_dict, self.config, strict=strict_load)
+        else:
+            self._packed_cpu = pack_depthanything_v2(state_dict, self.config, strict=strict_load)
         self._dev_weights: dict[str, torch.Tensor] = {}
         self._handle = None
         self._device = None
@@ -152,7 +168,7 @@ class DPTModel(torch.nn.Module):
         self._release()
         with torch.cuda.device(self._device):
             cfg = N.DptConfig()
-            cfg.variant = N.VARIANT_DINOV2
+            cfg.variant = N.VARIANT_BEIT if self.model_type == "beit" else N.VARIANT_DINOV2
             cfg.dtype = _TORCH_TO_DPT[self._dtype]
             cfg.features_per_token = self.config["features_per_token"]
             cfg.num_heads = self.config["num_heads"]

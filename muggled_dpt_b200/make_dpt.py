@@ -12,7 +12,11 @@ from time import sleep
 import torch
 
 from .dpt_model import DPTModel
-from .weights import determine_model_type_from_state_dict, get_model_config_from_state_dict
+from .weights import (
+    determine_model_type_from_state_dict,
+    get_model_config_from_midas_beit_state_dict,
+    get_model_config_from_state_dict,
+)
 
 
 def make_dpt_from_state_dict(
@@ -32,6 +36,8 @@ def make_dpt_from_state_dict(
     if model_type not in known_model_types:
         print("Accepted model types:", *known_model_types, sep="\n")
         raise NotImplementedError(f"Bad model type: {model_type}, no support for this yet!")
+    if model_type == "beit":
+        return make_beit_dpt_from_midas_v31_state_dict(state_dict, enable_cache, enable_optimizations, strict_load)
     if model_type != "depthanythingv2":
         raise NotImplementedError(
             f"Model type {model_type} is recognised but its B200 encoder is not built yet (SURVEY.md section 8: configs W/E, 8f)"
@@ -60,4 +66,20 @@ def make_depthanythingv2_dpt_from_original_state_dict(
               "  Some weights may be missing or unused!", sep="\n", flush=True)
     config_dict = get_model_config_from_state_dict(state_dict, enable_cache, enable_optimizations)
     model = DPTModel(config_dict, state_dict, strict_load=strict_load)
+    return config_dict, model
+
+
+def make_beit_dpt_from_midas_v31_state_dict(
+    midas_v31_state_dict: dict,
+    enable_cache: bool = False,
+    enable_optimizations: bool = True,
+    strict_load: bool = True,
+) -> tuple[dict, DPTModel]:
+    """make_beit_dpt.py:24-58. The relative position bias is always rebuilt per grid size on the device (the
+    reference's optional cache, v31_beit/image_encoder_model.py:93-119, has no observable effect on results)."""
+    if not strict_load:
+        print("", "WARNING:", "  Loading model weights without 'strict' mode enabled!",
+              "  Some weights may be missing or unused!", sep="\n", flush=True)
+    config_dict = get_model_config_from_midas_beit_state_dict(midas_v31_state_dict, enable_cache, enable_optimizations)
+    model = DPTModel(config_dict, midas_v31_state_dict, strict_load=strict_load, model_type="beit")
     return config_dict, model

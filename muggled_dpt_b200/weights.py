@@ -218,3 +218,133 @@ def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
         raise RuntimeError("Error(s) in loading state_dict: Missing key(s): " + ", ".join(missing[:8]) +
                            (" ..." if len(missing) > 8 else ""))
     return out
+
+
+# =====================================================================================================================
+# MiDaS v3.1 BEiT (muggled_dpt/v31_beit/state_dict_conversion/*): config inference + packing
+# =====================================================================================================================
+
+
+def get_model_config_from_midas_beit_state_dict(state_dict: dict, enable_cache: bool, enable_optimizations: bool) -> dict:
+    """config_from_midas_state_dict.py:17-40 - same keys, same order as the reference's BEiT config dict"""
+    def need(key):
+        assert key in state_dict, f"Error determining model config! Couldn't find {key} key"
+        return state_dict[key]
+
+    pe = need("pretrained.model.patch_embed.proj.weight")
+    block_ids = [int(m.group(1)) for m in (re.match(r"pretrained\.model\.blocks\.(\d+)\.", k) for k in state_dict) if m]
+    assert block_ids and max(block_ids) > 0, "Error determining number of transformer blocks! Could not find any blocks"
+    table = need("pretrained.model.blocks.0.attn.relative_position_bias_table")
+    side = int(math.isqrt(int(table.shape[0]) - 3))  # 2g - 1
+    base = (side + 1) // 2
+    return {
+        "features_per_token": int(pe.shape[0]),
+        "num_blocks": 1 + max(block_ids),
+        "num_heads": int(table.shape[1]),
+        "reassembly_features_list": [int(need(f"scratch.layer{i}_rn.weight").shape[1]) for i in (1, 2, 3, 4)],
+        "fusion_channels": int(need("scratch.layer1_rn.weight").shape[0]),
+        "patch_size_px": int(pe.shape[3]),
+        "base_patch_grid_hw": (base, base),
+        "enable_cache": enable_cache,
+        "enable_optimizations": enable_optimizations,
+    }
+
+
+def pack_beit(sd: dict, cfg: dict, strict: bool = True) -> dict:
+    """Returns {packed name: (fp32 cpu tensor, kind)}. Dropped like the reference does
+    (convert_midas_state_dict_keys.py:160-162,264): `relative_position_index`, `scratch.refinenet4.resConfUnit1.*`.
+    q_bias / v_bias become the bias of the fused QKV GEMM ([q_bias, 0, v_bias]; K has none - image_encoder_model.py:341)."""
+    F = cfg["features_per_token"]
+    L = cfg["num_blocks"]
+    missing = []
+
+    def get(key):
+        if key in sd:
+            return sd[key].detach().to(torch.float32).cpu()
+        missing.append(key)
+        return None
+
+    out = {}
+
+    def put(name, t, kind):
+        if t is not None:
+            out[name] = (t.contiguous(), kind)
+
+    def lin(key):
+        w = get(key)
+        return pack_linear(w.reshape(w.shape[0], -1)) if w is not None else None
+
+    def conv(key):
+        w = get(key)
+        return pack_conv(w) if w is not None else None
+
+    pw = get("pretrained.model.patch_embed.proj.weight")
+    put("patch.w", pack_patch_embed(pw) if pw is not None else None, "half")
+    put("patch.b", get("pretrained.model.patch_embed.proj.bias"), "f32")
+    cls = get("pretrained.model.cls_token")
+    put("beit.cls", cls.reshape(-1) if cls is not None else None, "f32")
+    for i in range(L):
+        s, d = f"pretrained.model.blocks.{i}.", f"blk{i}."
+        put(d + "ln1.w", get(s + "norm1.weight"), "f32")
+        put(d + "ln1.b", get(s + "norm1.bias"), "f32")
+        put(d + "ln2.w", get(s + "norm2.weight"), "f32")
+        put(d + "ln2.b", get(s + "norm2.bias"), "f32")
+        put(d + "qkv.w", lin(s + "attn.qkv.weight"), "half")
+        qb, vb = get(s + "attn.q_bias"), get(s + "attn.v_bias")
+        if qb is not None and vb is not None:
+            put(d + "qkv.b", torch.cat([qb.reshape(-1), torch.zeros(F), vb.reshape(-1)]), "f32")
+        put(d + "relpos.table", get(s + "attn.relative_position_bias_table"), "f32")
+        g1, g2 = get(s + "gamma_1"), get(s + "gamma_2")
+        w, b = get(s + "attn.proj.weight"), get(s + "attn.proj.bias")
+        if all(t is not None for t in (g1, w, b)):
+            put(d + "proj.w", pack_linear(g1[:, None] * w), "half")
+            put(d + "proj.b", g1 * b, "f32")
+        put(d + "fc1.w", lin(s + "mlp.fc1.weight"), "half")
+        put(d + "fc1.b", get(s + "mlp.fc1.bias"), "f32")
+        w, b = get(s + "mlp.fc2.weight"), get(s + "mlp.fc2.bias")
+        if all(t is not None for t in (g2, w, b)):
+            put(d + "fc2.w", pack_linear(g2[:, None] * w), "half")
+            put(d + "fc2.b", g2 * b, "f32")
+
+    for k in range(4):
+        s, d = f"pretrained.act_postprocess{k + 1}.", f"reasm{k}."
+        w = get(s + "0.project.0.weight")  # Linear(2F, F) on [patch, cls] (readout_projection.py:74-79)
+        if w is not None:
+            put(d + "readout.w1", pack_linear(w[:, :F]), "half")
+            put(d + "readout.w2", w[:, F:].clone(), "f32")
+        put(d + "readout.b", get(s + "0.project.0.bias"), "f32")
+        put(d + "proj.w", lin(s + "3.weight"), "half")
+        put(d + "proj.b", get(s + "3.bias"), "f32")
+        if k in (0, 1):
+            w = get(s + "4.weight")
+            put(d + "up.w", pack_conv_transpose(w) if w is not None else None, "half")
+            put(d + "up.b", get(s + "4.bias"), "f32")
+        elif k == 3:
+            put(d + "down.w", conv(s + "4.weight"), "half")
+            put(d + "down.b", get(s + "4.bias"), "f32")
+        put(d + "fuse.w", conv(f"scratch.layer{k + 1}_rn.weight"), "half")
+
+    for lvl in range(4):
+        s, d = f"scratch.refinenet{lvl + 1}.", f"fus{lvl}."
+        units = (("rcu1", "resConfUnit1"), ("rcu2", "resConfUnit2")) if lvl < 3 else (("rcu2", "resConfUnit2"),)
+        for dn, sn in units:
+            for cv in (1, 2):
+                put(f"{d}{dn}.c{cv}.w", conv(f"{s}{sn}.conv{cv}.weight"), "half")
+                put(f"{d}{dn}.c{cv}.b", get(f"{s}{sn}.conv{cv}.bias"), "f32")
+        put(d + "out.w", lin(s + "out_conv.weight"), "half")
+        put(d + "out.b", get(s + "out_conv.bias"), "f32")
+
+    put("head.c1.w", conv("scratch.output_conv.0.weight"), "half")
+    put("head.c1.b", get("scratch.output_conv.0.bias"), "f32")
+    put("head.c2.w", conv("scratch.output_conv.2.weight"), "half")
+    put("head.c2.b", get("scratch.output_conv.2.bias"), "f32")
+    w = get("scratch.output_conv.4.weight")
+    put("head.c3.w_host", w.reshape(-1) if w is not None else None, "host")
+    put("head.c3.b_host", get("scratch.output_conv.4.bias"), "host")
+
+    if missing:
+        if strict:
+            raise RuntimeError("Error(s) in loading state_dict: Missing key(s): " + ", ".join(missing[:8]) +
+                               (" ..." if len(missing) > 8 else ""))
+        raise RuntimeError("non-strict loading of BEiT checkpoints with missing keys is not supported: " + missing[0])
+    return out

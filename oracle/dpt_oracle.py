@@ -270,3 +270,229 @@ def make_synthetic_state_dict(name: str = "vits", seed: int = 0, base_grid: int 
 def make_input(B: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
     g = torch.Generator().manual_seed(1000 + seed)
     return torch.randn(B, 3, H, W, generator=g)
+
+
+# =====================================================================================================================
+# MiDaS v3.1 BEiT: upstream keys `pretrained.model.*`, `pretrained.act_postprocess*`,
+# `scratch.*`
+# =====================================================================================================================
+
+
+def infer_config_beit(sd: dict) -> dict:
+    """v31_beit/state_dict_conversion/config_from_midas_state_dict.py (heads from the bias-table width :67-80, base grid
+    from its length :205-246)"""
+    feats = int(sd["pretrained.model.patch_embed.proj.weight"].shape[0])
+    patch = int(sd["pretrained.model.patch_embed.proj.weight"].shape[3])
+    blocks = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("pretrained.model.blocks."))
+    table = sd["pretrained.model.blocks.0.attn.relative_position_bias_table"]
+    heads = int(table.shape[1])
+    side = int(math.isqrt(int(table.shape[0]) - 3))  # (2g-1)
+    base = (side + 1) // 2
+    return {
+        "features_per_token": feats,
+        "num_blocks": blocks,
+        "num_heads": heads,
+        "reassembly_features_list": [int(sd[f"scratch.layer{i}_rn.weight"].shape[1]) for i in (1, 2, 3, 4)],
+        "fusion_channels": int(sd["scratch.layer1_rn.weight"].shape[0]),
+        "patch_size_px": patch,
+        "base_patch_grid_hw": (base, base),
+    }
+
+
+def beit_relative_position_index(grid_hw) -> torch.Tensor:
+    """RelativePositionEncoding._generate_relative_position_index - v31_beit/components/relative_positional_encoder.py:117-238"""
+    gh, gw = grid_hw
+    n = gh * gw + 1
+    ys, xs = torch.meshgrid(torch.arange(gh), torch.arange(gw), indexing="ij")
+    coords = torch.stack((ys.flatten(), xs.flatten()))  # [2, g]
+    rel = coords[:, :, None] - coords[:, None, :]
+    idx_tok = (rel[0] + gh - 1) * (2 * gw - 1) + (rel[1] + gw - 1)
+    max_idx = (2 * gh - 1) * (2 * gw - 1) - 1
+    idx = torch.zeros((n, n), dtype=torch.long)
+    idx[1:, 1:] = idx_tok
+    idx[0, :] = max_idx + 1  # cls -> token
+    idx[:, 0] = max_idx + 2  # token -> cls
+    idx[0, 0] = max_idx + 3  # cls -> cls
+    return idx
+
+
+def beit_position_bias(table: torch.Tensor, base_hw, grid_hw) -> torch.Tensor:
+    """_generate_position_bias_lut - relative_positional_encoder.py:242-309 (bilinear, align_corners=False) -> [H,N,N]"""
+    heads = table.shape[1]
+    rh, rw = 2 * base_hw[0] - 1, 2 * base_hw[1] - 1
+    nh, nw = 2 * grid_hw[0] - 1, 2 * grid_hw[1] - 1
+    tok, cls = table[: rh * rw], table[rh * rw:]
+    t2d = tok.reshape(1, rh, rw, heads).permute(0, 3, 1, 2)
+    t2d = F.interpolate(t2d, size=(nh, nw), mode="bilinear")
+    lut = torch.cat([t2d.permute(0, 2, 3, 1).reshape(nh * nw, heads), cls])
+    n = grid_hw[0] * grid_hw[1] + 1
+    return lut[beit_relative_position_index(grid_hw).reshape(-1)].reshape(n, n, heads).permute(2, 0, 1).contiguous()
+
+
+def beit_block(sd: dict, i: int, x: torch.Tensor, heads: int, base_hw, grid_hw):
+    """TransformerBlock / SelfAttentionRelPos - v31_beit/image_encoder_model.py:233-251,311-356"""
+    pre = f"pretrained.model.blocks.{i}."
+    B, N, C = x.shape
+    d = C // heads
+    t = F.layer_norm(x, (C,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-6)
+    qkv = F.linear(t, sd[pre + "attn.qkv.weight"]).reshape(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.unbind(0)
+    q = (q + sd[pre + "attn.q_bias"].reshape(1, heads, 1, d)) * d**-0.5
+    v = v + sd[pre + "attn.v_bias"].reshape(1, heads, 1, d)
+    a = q @ k.transpose(-2, -1) + beit_position_bias(sd[pre + "attn.relative_position_bias_table"], base_hw, grid_hw)
+    o = (a.softmax(dim=-1) @ v).transpose(1, 2).reshape(B, N, C)
+    o = F.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+    x = x + sd[pre + "gamma_1"] * o
+    t = F.layer_norm(x, (C,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-6)
+    m = F.linear(F.gelu(F.linear(t, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])),
+                 sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    return x + sd[pre + "gamma_2"] * m
+
+
+def beit_encoder(sd: dict, cfg: dict, tokens: torch.Tensor, grid_hw):
+    """BEiTModel4Stage.forward - v31_beit/image_encoder_model.py:68-91 (no position embedding, no output norm)"""
+    x = torch.cat((sd["pretrained.model.cls_token"].expand(tokens.shape[0], -1, -1), tokens), dim=1)
+    per_stage = int(round(cfg["num_blocks"] / 4))
+    taps = []
+    for i in range(cfg["num_blocks"]):
+        x = beit_block(sd, i, x, cfg["num_heads"], cfg["base_patch_grid_hw"], grid_hw)
+        if (i + 1) % per_stage == 0:
+            taps.append(x)
+    return tuple(taps[:4])
+
+
+def beit_reassemble(sd: dict, taps, grid_hw):
+    """ReassembleBlock.forward - v31_beit/reassembly_model.py:118-128 + ReadoutProjectLayer (readout_projection.py)"""
+    outs = []
+    for k, t in enumerate(taps):
+        p = f"pretrained.act_postprocess{k + 1}."
+        cat = torch.cat((t[:, 1:], t[:, :1].expand(-1, t.shape[1] - 1, -1)), dim=-1)  # [patch, cls] (:74-79)
+        x = F.gelu(F.linear(cat, sd[p + "0.project.0.weight"], sd[p + "0.project.0.bias"]))
+        x = x.transpose(1, 2).unflatten(2, tuple(grid_hw))
+        x = F.conv2d(x, sd[p + "3.weight"], sd[p + "3.bias"])
+        if k in (0, 1):
+            x = F.conv_transpose2d(x, sd[p + "4.weight"], sd[p + "4.bias"], stride=4 if k == 0 else 2)
+        elif k == 3:
+            x = F.conv2d(x, sd[p + "4.weight"], sd[p + "4.bias"], stride=2, padding=1)
+        outs.append(F.conv2d(x, sd[f"scratch.layer{k + 1}_rn.weight"], None, padding=1))
+    return tuple(outs)
+
+
+def _midas_fusion(sd: dict, r1, r2, r3, r4):
+    """FusionModel.forward - v31_beit/fusion_model.py (same structure as the Depth-Anything one, `scratch.` prefix)"""
+    def rcu(pre, x):
+        y = F.conv2d(F.relu(x), sd[pre + "conv1.weight"], sd[pre + "conv1.bias"], padding=1)
+        y = F.conv2d(F.relu(y), sd[pre + "conv2.weight"], sd[pre + "conv2.bias"], padding=1)
+        return y + x
+
+    def up(rn, x):
+        x = rcu(rn + "resConfUnit2.", x)
+        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        return F.conv2d(x, sd[rn + "out_conv.weight"], sd[rn + "out_conv.bias"])
+
+    f = up("scratch.refinenet4.", r4)
+    for idx, r in ((3, r3), (2, r2), (1, r1)):
+        rn = f"scratch.refinenet{idx}."
+        f = up(rn, rcu(rn + "resConfUnit1.", r) + f)
+    return f
+
+
+def _midas_head(sd: dict, x: torch.Tensor):
+    """MonocularDepthHead.forward - v31_beit/head_model.py:37-74 (x2 upsample)"""
+    x = F.conv2d(x, sd["scratch.output_conv.0.weight"], sd["scratch.output_conv.0.bias"], padding=1)
+    x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    x = F.relu(F.conv2d(x, sd["scratch.output_conv.2.weight"], sd["scratch.output_conv.2.bias"], padding=1))
+    x = F.relu(F.conv2d(x, sd["scratch.output_conv.4.weight"], sd["scratch.output_conv.4.bias"]))
+    return x.squeeze(1)
+
+
+def forward_beit(sd: dict, img_bchw: torch.Tensor, cfg: dict | None = None, return_stages: bool = False):
+    cfg = cfg or infer_config_beit(sd)
+    with torch.inference_mode():
+        w, b = sd["pretrained.model.patch_embed.proj.weight"], sd["pretrained.model.patch_embed.proj.bias"]
+        x = F.conv2d(img_bchw, w, b, stride=w.shape[-1])  # v31_beit/patch_embed.py:74-91
+        grid_hw = tuple(x.shape[2:])
+        tokens = x.flatten(2).transpose(1, 2)
+        taps = beit_encoder(sd, cfg, tokens, grid_hw)
+        maps = beit_reassemble(sd, taps, grid_hw)
+        fused = _midas_fusion(sd, *maps)
+        depth = _midas_head(sd, fused)
+    if return_stages:
+        return {"tokens": tokens, "taps": taps, "maps": maps, "fused": fused, "depth": depth, "grid_hw": grid_hw}
+    return depth
+
+
+BEIT_CONFIGS = {
+    # make_beit_dpt.py docstring
+    "beit_large_384": dict(F=1024, heads=16, blocks=24, reasm=(256, 512, 1024, 1024), C=256, base=24),
+    "beit_base_384": dict(F=768, heads=12, blocks=12, reasm=(96, 192, 384, 768), C=256, base=24),
+    "beit_tiny": dict(F=128, heads=2, blocks=4, reasm=(16, 32, 64, 128), C=32, base=6),
+}
+
+
+def make_synthetic_state_dict_beit(name: str = "beit_tiny", seed: int = 0) -> dict:
+    """MiDaS v3.1 BEiT key schema, fan-in scaled weights"""
+    cfg = BEIT_CONFIGS[name]
+    Fd, H, L, R, C, g0 = cfg["F"], cfg["heads"], cfg["blocks"], cfg["reasm"], cfg["C"], cfg["base"]
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    def fan(*shape):
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        return rn(*shape, std=fan_in**-0.5)
+
+    sd = {}
+    sd["pretrained.model.cls_token"] = rn(1, 1, Fd, std=0.5)
+    sd["pretrained.model.patch_embed.proj.weight"] = fan(Fd, 3, 16, 16)
+    sd["pretrained.model.patch_embed.proj.bias"] = rn(Fd, std=0.1)
+    for i in range(L):
+        p = f"pretrained.model.blocks.{i}."
+        sd[p + "gamma_1"] = 0.05 + 0.95 * torch.rand(Fd, generator=g)
+        sd[p + "gamma_2"] = 0.05 + 0.95 * torch.rand(Fd, generator=g)
+        for nrm in ("norm1", "norm2"):
+            sd[p + nrm + ".weight"] = 1.0 + rn(Fd, std=0.1)
+            sd[p + nrm + ".bias"] = rn(Fd, std=0.1)
+        sd[p + "attn.q_bias"] = rn(Fd, std=0.2)
+        sd[p + "attn.v_bias"] = rn(Fd, std=0.2)
+        sd[p + "attn.qkv.weight"] = fan(3 * Fd, Fd) * 1.5
+        sd[p + "attn.relative_position_bias_table"] = rn((2 * g0 - 1) ** 2 + 3, H, std=1.0)
+        sd[p + "attn.relative_position_index"] = torch.zeros(g0 * g0 + 1, g0 * g0 + 1, dtype=torch.long)  # dropped
+        sd[p + "attn.proj.weight"] = fan(Fd, Fd)
+        sd[p + "attn.proj.bias"] = rn(Fd, std=0.1)
+        sd[p + "mlp.fc1.weight"] = fan(4 * Fd, Fd)
+        sd[p + "mlp.fc1.bias"] = rn(4 * Fd, std=0.1)
+        sd[p + "mlp.fc2.weight"] = fan(Fd, 4 * Fd)
+        sd[p + "mlp.fc2.bias"] = rn(Fd, std=0.1)
+    for k in range(4):
+        p = f"pretrained.act_postprocess{k + 1}."
+        sd[p + "0.project.0.weight"] = fan(Fd, 2 * Fd) * 1.4
+        sd[p + "0.project.0.bias"] = rn(Fd, std=0.1)
+        sd[p + "3.weight"] = fan(R[k], Fd, 1, 1) * 1.5
+        sd[p + "3.bias"] = rn(R[k], std=0.1)
+    sd["pretrained.act_postprocess1.4.weight"] = rn(R[0], R[0], 4, 4, std=R[0] ** -0.5)
+    sd["pretrained.act_postprocess1.4.bias"] = rn(R[0], std=0.1)
+    sd["pretrained.act_postprocess2.4.weight"] = rn(R[1], R[1], 2, 2, std=R[1] ** -0.5)
+    sd["pretrained.act_postprocess2.4.bias"] = rn(R[1], std=0.1)
+    sd["pretrained.act_postprocess4.4.weight"] = fan(R[3], R[3], 3, 3)
+    sd["pretrained.act_postprocess4.4.bias"] = rn(R[3], std=0.1)
+    for k in range(4):
+        sd[f"scratch.layer{k + 1}_rn.weight"] = fan(C, R[k], 3, 3)
+    for i in (1, 2, 3, 4):
+        for u in (1, 2):
+            for cv in (1, 2):
+                p = f"scratch.refinenet{i}.resConfUnit{u}.conv{cv}."
+                sd[p + "weight"] = fan(C, C, 3, 3) * (1.4 if cv == 1 else 0.7)
+                sd[p + "bias"] = rn(C, std=0.1)
+        sd[f"scratch.refinenet{i}.out_conv.weight"] = fan(C, C, 1, 1)
+        sd[f"scratch.refinenet{i}.out_conv.bias"] = rn(C, std=0.1)
+    sd["scratch.output_conv.0.weight"] = fan(C // 2, C, 3, 3)
+    sd["scratch.output_conv.0.bias"] = rn(C // 2, std=0.1)
+    sd["scratch.output_conv.2.weight"] = fan(32, C // 2, 3, 3) * 1.4
+    sd["scratch.output_conv.2.bias"] = rn(32, std=0.1) + 0.2
+    sd["scratch.output_conv.4.weight"] = fan(1, 32, 1, 1)
+    sd["scratch.output_conv.4.bias"] = torch.full((1,), 2.0)
+    return sd

@@ -102,13 +102,34 @@ def main():
         print(f"vits_{tag}: depth std {ref['depth'].std().item():.4f} mean {ref['depth'].mean().item():.4f} "
               f"min {ref['depth'].min().item():.4f}; taps std {[round(t.std().item(), 3) for t in ref['taps']]}")
 
+    # ---- MiDaS v3.1 BEiT (tiny synthetic config; everything stored except the checkpoint, regenerated from its seed)
+    for tag, (B, H, W) in {"a": (2, 96, 96), "b": (1, 96, 128)}.items():  # a: base grid (LUT resize = identity)
+        sd = O.make_synthetic_state_dict_beit("beit_tiny", seed=5)
+        img = O.make_input(B, H, W, seed=3)
+        cfg, ref = run_reference(sd, img, enable_optimizations=True)
+        fix = {
+            "model_type": "beit",
+            "config": {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in cfg.items()},
+            "sd_seed": 5, "sd_name": "beit_tiny", "sd_checksum": state_dict_checksum(sd),
+            "img": img,
+            "tokens": ref["tokens"], "taps": list(ref["taps"]), "maps": list(ref["maps"]),
+            "fused": ref["fused"], "depth": ref["depth"], "grid_hw": ref["grid_hw"],
+        }
+        torch.save(fix, os.path.join(out_dir, f"beit_tiny_{tag}.pt"))
+        print(f"beit_tiny_{tag}: depth std {ref['depth'].std().item():.4f} mean {ref['depth'].mean().item():.4f}; "
+              f"taps std {[round(t.std().item(), 3) for t in ref['taps']]}")
+
     # ---- oracle vs reference, right here
     for name in sorted(os.listdir(out_dir)):
         if not name.endswith(".pt"):
             continue
         fix = torch.load(os.path.join(out_dir, name))
-        sd = fix.get("state_dict") or O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"])
-        st = O.forward(sd, fix["img"], return_stages=True)
+        if fix.get("model_type") == "beit":
+            sd = O.make_synthetic_state_dict_beit(fix["sd_name"], fix["sd_seed"])
+            st = O.forward_beit(sd, fix["img"], return_stages=True)
+        else:
+            sd = fix.get("state_dict") or O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"])
+            st = O.forward(sd, fix["img"], return_stages=True)
         print(name, "oracle-vs-reference depth max abs diff:", (st["depth"] - fix["depth"]).abs().max().item())
 
 

@@ -171,3 +171,59 @@ def test_inference_entry_point_bgr_image():
     out = model.inference(bgr, max_side_length=112, use_square_sizing=True)
     assert tuple(out.shape) == (1, 112, 112) and out.dtype == torch.bfloat16
     assert torch.isfinite(out.float()).all()
+
+
+# ------------------------------------------------------------------------------------------------ MiDaS v3.1 BEiT
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("name", ["beit_tiny_a.pt", "beit_tiny_b.pt"])
+def test_beit_tiny_stagewise_against_reference_golden(name, dtype):
+    from oracle import dpt_oracle as O
+
+    fix = torch.load(os.path.join(GOLDEN, name))
+    sd = O.make_synthetic_state_dict_beit(fix["sd_name"], fix["sd_seed"])
+    cfg, model = _load_model(sd, dtype, name="dpt_beit_synth.pt")
+    assert model.model_type == "beit"
+    img = fix["img"].to("cuda", dtype)
+    report = {}
+    with torch.inference_mode():
+        tokens, grid_hw = model.patch_embed(img)
+        assert tuple(grid_hw) == tuple(fix["grid_hw"])
+        report["tokens"] = _err(tokens, fix["tokens"])
+        taps = model.imgencoder(fix["tokens"].to("cuda", dtype), grid_hw)
+        for i in range(4):
+            report[f"tap{i}"] = _err(taps[i], fix["taps"][i])
+        maps = model.reassemble(*[t.to("cuda", dtype) for t in fix["taps"]], grid_hw)
+        for i in range(4):
+            assert tuple(maps[i].shape) == tuple(fix["maps"][i].shape)
+            report[f"map{i}"] = _err(maps[i], fix["maps"][i])
+        fused = model.fusion(*[t.to("cuda", dtype) for t in fix["maps"]])
+        report["fused"] = _err(fused, fix["fused"])
+        depth = model.head(fix["fused"].to("cuda", dtype))
+        report["head"] = _err(depth, fix["depth"])
+        full = model(img)
+        assert tuple(full.shape) == tuple(fix["depth"].shape)
+        report["depth_e2e"] = _err(full, fix["depth"])
+    for k, v in report.items():
+        print(f"{name} {dtype} {k}: rel_l2={v[0]:.3e} max_abs={v[1]:.3e} max_rel={v[2]:.3e}")
+    for k, v in report.items():
+        tol = REL_L2[dtype] * (2.0 if k == "depth_e2e" else 1.0)
+        assert v[0] < tol, (k, v)
+
+
+def test_beit_base_384_against_oracle():
+    """config E shape family (BASELINE.json configs[4]): BEiT at 384x384 (24x24 grid, 577 tokens, bias attention),
+    here the 12-block base model with batch 2, vs the fp32 oracle"""
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict_beit("beit_base_384", seed=9)
+    img = O.make_input(2, 384, 384, seed=4)
+    ref = O.forward_beit(sd, img)
+    cfg, model = _load_model(sd, torch.bfloat16, name="dpt_beit_base_384.pt")
+    with torch.inference_mode():
+        depth = model(img.to("cuda", torch.bfloat16))
+    e = _err(depth, ref)
+    print(f"beit_base_384 bf16: rel_l2={e[0]:.3e} max_abs={e[1]:.3e} max_rel={e[2]:.3e}")
+    assert tuple(depth.shape) == (2, 384, 384)
+    assert e[0] < 2 * REL_L2[torch.bfloat16], e

@@ -66,3 +66,30 @@ def test_oracle_rejects_odd_grid_like_the_reference():
     sd = O.make_synthetic_state_dict("tiny", seed=3, base_grid=5)
     with pytest.raises(RuntimeError):
         O.forward(sd, O.make_input(1, 42, 42))
+
+
+@pytest.mark.parametrize("name", ["beit_tiny_a.pt", "beit_tiny_b.pt"])
+def test_beit_oracle_matches_reference_every_stage(name):
+    from oracle.make_golden import state_dict_checksum
+
+    fix = torch.load(os.path.join(GOLDEN, name))
+    sd = O.make_synthetic_state_dict_beit(fix["sd_name"], fix["sd_seed"])
+    assert state_dict_checksum(sd) == fix["sd_checksum"]
+    st = O.forward_beit(sd, fix["img"], return_stages=True)
+    assert tuple(st["grid_hw"]) == tuple(fix["grid_hw"])
+    torch.testing.assert_close(st["tokens"], fix["tokens"], rtol=0, atol=1e-6)
+    for a, b in zip(st["taps"], fix["taps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=5e-5)
+    for a, b in zip(st["maps"], fix["maps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-4)
+    torch.testing.assert_close(st["depth"], fix["depth"], rtol=0, atol=2e-4)
+
+
+def test_beit_relative_position_index_special_rows():
+    idx = O.beit_relative_position_index((3, 4))
+    n = 13
+    top = (2 * 3 - 1) * (2 * 4 - 1) - 1
+    assert idx.shape == (n, n)
+    assert (idx[0, 1:] == top + 1).all() and (idx[1:, 0] == top + 2).all() and idx[0, 0] == top + 3
+    assert idx[1:, 1:].min() == 0 and idx[1:, 1:].max() == top
+    assert (idx[1:, 1:].diagonal() == (3 - 1) * (2 * 4 - 1) + (4 - 1)).all()  # zero offset

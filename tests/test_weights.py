@@ -126,3 +126,43 @@ def test_factory_surface_on_cpu():
         model.to("cpu")
     with pytest.raises(RuntimeError):
         model.to(dtype=torch.float32)
+
+
+def test_beit_config_and_packing():
+    sd = O.make_synthetic_state_dict_beit("beit_tiny", seed=5)
+    cfg = Wt.get_model_config_from_midas_beit_state_dict(sd, False, True)
+    assert list(cfg.keys()) == ["features_per_token", "num_blocks", "num_heads", "reassembly_features_list",
+                                "fusion_channels", "patch_size_px", "base_patch_grid_hw", "enable_cache",
+                                "enable_optimizations"]
+    ocfg = O.infer_config_beit(sd)
+    for k, v in ocfg.items():
+        assert cfg[k] == v, k
+    packed = Wt.pack_beit(sd, cfg)
+    # q/v bias -> fused QKV bias with a zero K part (v31_beit/image_encoder_model.py:341-342)
+    qkv_b = packed["blk2.qkv.b"][0]
+    Fd = cfg["features_per_token"]
+    assert torch.equal(qkv_b[:Fd], sd["pretrained.model.blocks.2.attn.q_bias"])
+    assert torch.count_nonzero(qkv_b[Fd:2 * Fd]) == 0
+    assert torch.equal(qkv_b[2 * Fd:], sd["pretrained.model.blocks.2.attn.v_bias"])
+    # readout split: W1 patch + W2 cls + b == Linear(2F,F)(cat(patch, cls))
+    torch.manual_seed(0)
+    patch, cls = torch.randn(5, Fd), torch.randn(1, Fd)
+    W = sd["pretrained.act_postprocess2.0.project.0.weight"]
+    b = sd["pretrained.act_postprocess2.0.project.0.bias"]
+    ref = F.linear(torch.cat([patch, cls.expand(5, -1)], dim=-1), W, b)
+    got = patch @ packed["reasm1.readout.w1"][0][:, :Fd].t() + cls @ packed["reasm1.readout.w2"][0].t() + packed["reasm1.readout.b"][0]
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    assert not any("relative_position_index" in k for k in packed)
+    assert not any(k.startswith("fus3.rcu1") for k in packed)
+
+
+def test_beit_factory_surface_on_cpu():
+    from muggled_dpt_b200 import make_dpt_from_state_dict
+
+    sd = O.make_synthetic_state_dict_beit("beit_tiny", seed=5)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "dpt_beit_tiny.pt")
+        torch.save(sd, path)
+        cfg, model = make_dpt_from_state_dict(path)
+    assert model.model_type == "beit" and cfg["num_heads"] == 2 and cfg["base_patch_grid_hw"] == (6, 6)
+    assert model.patch_embed.rgb_offset == (0.5, 0.5, 0.5)
