@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--model", default="vitl", choices=["vitl", "vitb", "vits", "tiny"])
+    ap.add_argument("--model", default="vitl",
+                    choices=["vitl", "vitb", "vits", "tiny", "beit_large_384", "beit_base_384", "beit_tiny"])
     ap.add_argument("--batch", type=int, default=32, help="global batch (frames per step)")
     ap.add_argument("--size", type=int, default=504)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
@@ -64,7 +65,8 @@ def load_peaks():
 
 def algorithmic_gflop_per_frame(model, size):
     """BASELINE.md section 3 (torch flop counter on the reference modules, 2*MAC, matmul/conv only)."""
-    table = {("vits", 504): 107.32, ("vitb", 504): 356.69, ("vitl", 504): 1224.94, ("vitl", 532): 1385.8}
+    table = {("vits", 504): 107.32, ("vitb", 504): 356.69, ("vitl", 504): 1224.94, ("vitl", 532): 1385.8,
+             ("beit_large_384", 384): 516.41}
     return table.get((model, size))
 
 
@@ -120,6 +122,18 @@ class ClockSampler:
         return out
 
 
+def _oracle_model(O, model_name):
+    """(synthetic upstream-format checkpoint, oracle forward) for a model name"""
+    if model_name.startswith("beit"):
+        return O.make_synthetic_state_dict_beit(model_name, seed=11), O.forward_beit
+    return O.make_synthetic_state_dict(model_name, seed=11), O.forward
+
+
+def _checkpoint_file_name(model_name):
+    # the reference sniffs Depth-Anything v1/v2 from the FILE NAME (make_dpt.py:98-104)
+    return f"dpt_{model_name}_synthetic.pt" if model_name.startswith("beit") else f"depth_anything_v2_{model_name}_synthetic.pth"
+
+
 def time_cpu_oracle(model_name, size, frames, threads=None):
     """fp32 CPU restatement of the reference path (oracle/), B=1 per step: returns (frames/s, cores, sample text)"""
     import torch
@@ -129,13 +143,13 @@ def time_cpu_oracle(model_name, size, frames, threads=None):
     if threads:
         torch.set_num_threads(threads)
     cores = torch.get_num_threads()
-    sd = O.make_synthetic_state_dict(model_name, seed=11)
+    sd, fwd = _oracle_model(O, model_name)
     img = O.make_input(1, size, size, seed=2)
-    O.forward(sd, img)  # warm-up
+    fwd(sd, img)  # warm-up
     ts = []
     for _ in range(frames):
         t0 = time.perf_counter()
-        O.forward(sd, img)
+        fwd(sd, img)
         ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
     sample = f"{frames} frames of B=1 {model_name} {size}x{size} fp32 after 1 warm-up, median; torch threads={cores} of {os.cpu_count()} cpus"
@@ -152,14 +166,14 @@ def run_reference(args, rank, world):
     from oracle import dpt_oracle as O
 
     cores = torch.get_num_threads()
-    sd = O.make_synthetic_state_dict(args.model, seed=11)
+    sd, fwd = _oracle_model(O, args.model)
     img = O.make_input(1, args.size, args.size, seed=2)
     for _ in range(max(1, min(args.warmup, 1))):
-        O.forward(sd, img)
+        fwd(sd, img)
     steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.forward(sd, img)
+        fwd(sd, img)
     dt = time.perf_counter() - t0
     fps = steps / dt
     sample = (f"each step = 1 frame (a bounded sample of the batch-{args.batch} workload) of {args.model} "
@@ -190,6 +204,7 @@ def main():
     import torch.distributed as dist
 
     from muggled_dpt_b200 import make_dpt_from_state_dict
+    from muggled_dpt_b200.distributed import all_gather_depth, shard_range
     from oracle import dpt_oracle as O  # synthetic checkpoint generator + cpu_baseline only
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
@@ -202,7 +217,8 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     if args.scaling == "strong":
         assert args.batch % world == 0, "global batch must divide over ranks"
-        b_local = args.batch // world
+        lo, hi = shard_range(args.batch, rank, world)
+        b_local = hi - lo
         b_global = args.batch
     else:
         b_local = args.batch
@@ -210,9 +226,9 @@ def main():
     S = args.size
 
     # ---- model (synthetic seeded checkpoint in the upstream format, loaded through the reference-shaped factory)
-    sd = O.make_synthetic_state_dict(args.model, seed=11)
+    sd, _ = _oracle_model(O, args.model)
     with tempfile.TemporaryDirectory() as td:
-        path = os.path.join(td, f"depth_anything_v2_{args.model}_synthetic.pth")
+        path = os.path.join(td, _checkpoint_file_name(args.model))
         torch.save(sd, path)
         del sd
         cfg, model = make_dpt_from_state_dict(path)
@@ -230,7 +246,7 @@ def main():
         flush.zero_()  # L2 flush between iterations (B200_PROFILING.md timing hygiene)
         model.forward_into(img, out)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            all_gather_depth(out, b_global, out=gathered)
 
     def barrier():
         if world > 1:
@@ -271,7 +287,7 @@ def main():
             def step_host():
                 model.forward_host(host_img, host_out)
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered, model._io[(b_local, S, S)][1])
+                    all_gather_depth(model._io[(b_local, S, S)][1], b_global, out=gathered)
             for _ in range(2):
                 step_host()
             ms_e2e = timed(step_host, args.steps)
@@ -337,8 +353,9 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
-                "workload": f"Depth-Anything-V2 {args.model} (synthetic seeded weights), global batch {b_global}, "
-                            f"3x{S}x{S} (reference's effective 518 setting), {args.dtype}",
+                "workload": (f"MiDaS v3.1 {args.model}" if args.model.startswith("beit") else f"Depth-Anything-V2 {args.model}")
+                            + f" (synthetic seeded weights), global batch {b_global}, 3x{S}x{S}"
+                            + (" (reference's effective 518 setting)" if S == 504 else "") + f", {args.dtype}",
                 "global_batch": b_global, "per_gpu_batch": b_local, "parallelism": f"dp{world} batch-shard + all-gather",
                 "l2": "256 MiB buffer rewritten between iterations (L2 flush); per-step working set >> 126 MB L2",
             },
