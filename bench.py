@@ -212,6 +212,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("DPT_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
@@ -320,10 +321,19 @@ def main():
             peaks = load_peaks()
             dom = max(agg.items(), key=lambda kv: kv[1][0])[0]
             a = agg[dom]
+            traffic, traffic_src = None, None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    tj = json.load(f).get(dom)
+                if tj and args.model == "vitl" and b_local == 32 and S == 504:
+                    traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+            except Exception:
+                pass
             if a[1] > 0:
                 ach = a[1] / (a[0] / 1000.0) / 1e12
                 roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"],
-                            "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                            "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
+                            "traffic_source": traffic_src, "algorithmic_bytes_per_launch": a[2] / a[3],
                             "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                             "avg_launch_ms": a[0] / a[3], "flop_per_launch": a[1] / a[3],
                             "share_of_step": a[0] / tot_ms}

@@ -496,3 +496,240 @@ def make_synthetic_state_dict_beit(name: str = "beit_tiny", seed: int = 0) -> di
     sd["scratch.output_conv.4.weight"] = fan(1, 32, 1, 1)
     sd["scratch.output_conv.4.bias"] = torch.full((1,), 2.0)
     return sd
+
+
+# =====================================================================================================================
+# MiDaS v3.1 SwinV2: hierarchical windowed cosine attention, post-norm blocks
+# =====================================================================================================================
+
+
+def infer_config_swinv2(sd: dict) -> dict:
+    """v31_swinv2/state_dict_conversion/config_from_midas_state_dict.py:17-214"""
+    f0 = int(sd["pretrained.model.patch_embed.proj.weight"].shape[0])
+    patch = int(sd["pretrained.model.patch_embed.proj.weight"].shape[3])
+    heads, layers = {}, {}
+    for k in sd:
+        if k.startswith("pretrained.model.layers.") and ".blocks." in k:
+            s, b = int(k.split(".")[3]), int(k.split(".")[5])
+            layers[s] = max(layers.get(s, 0), b + 1)
+            if k.endswith("logit_scale"):
+                heads[s] = int(sd[k].shape[0])
+    mask_key = sorted(k for k in sd if k.endswith("attn_mask"))[0]
+    nw, area = sd[mask_key].shape[:2]
+    win = int(math.isqrt(int(area)))
+    base = int(math.isqrt(int(nw) * int(area)))
+    pre_lut = {16: [16, 16, 16, 8], 24: [12, 12, 12, 6]}
+    return {
+        "features_per_stage": [f0 * 2**i for i in range(4)],
+        "heads_per_stage": [heads[i] for i in range(4)],
+        "layers_per_stage": [layers[i] for i in range(4)],
+        "base_patch_grid_hw": (base, base),
+        "window_size_hw": (win, win),
+        "pretrained_window_sizes_per_stage": pre_lut.get(win, [None] * 4),
+        "fusion_channels": int(sd["scratch.layer1_rn.weight"].shape[0]),
+        "patch_size_px": patch,
+    }
+
+
+def swin_window_and_shift(grid_hw, target_hw):
+    """adjust_window_and_shift_sizes - v31_swinv2/components/windowed_attention.py:345-388"""
+    out_win, out_shift = [], []
+    for patch, targ in zip(grid_hw, target_hw):
+        win = min(targ, patch)
+        if patch % win != 0:
+            divs = [d for d in range(win // 2, 2 * win) if patch % d == 0]
+            win = min(divs, key=lambda d: abs(patch - d))
+        out_win.append(win)
+        out_shift.append(0 if patch <= win else win // 2)
+    return tuple(out_win), tuple(out_shift)
+
+
+def swin_shift_mask(grid_hw, win_hw, shift_hw):
+    """make_shift_mask - windowed_attention.py:394-439 -> [nW, A, A] of 0 / -100 (None when no shift)"""
+    (gh, gw), (wh, ww), (sh, sw) = grid_hw, win_hw, shift_hw
+    if sh == 0 and sw == 0:
+        return None
+    img = torch.zeros((gh, gw))
+    cnt = 0
+    for hs in (slice(0, -wh), slice(-wh, -sh), slice(-sh, None)):
+        for ws in (slice(0, -ww), slice(-ww, -sw), slice(-sw, None)):
+            img[hs, ws] = cnt
+            cnt += 1
+    win = img.reshape(gh // wh, wh, gw // ww, ww).permute(0, 2, 1, 3).reshape(-1, wh * ww)
+    diff = win.unsqueeze(1) - win.unsqueeze(2)
+    return torch.where(diff != 0, torch.tensor(-100.0), torch.tensor(0.0))
+
+
+def swin_cpb_bias(sd: dict, pre: str, win_hw, pretrained_window):
+    """RelativePositionEncoding._get_position_bias - v31_swinv2/components/relative_positional_encoder.py:60-93,121-283"""
+    wh, ww = win_hw
+    ys = torch.arange(-(wh - 1), wh, dtype=torch.float32)
+    xs = torch.arange(-(ww - 1), ww, dtype=torch.float32)
+    table = torch.stack(torch.meshgrid([ys, xs], indexing="ij")).permute(1, 2, 0).contiguous()
+    table[:, :, 0] /= max((wh if pretrained_window is None else pretrained_window) - 1, 1)
+    table[:, :, 1] /= max((ww if pretrained_window is None else pretrained_window) - 1, 1)
+    table = torch.sign(table) * torch.log2(torch.abs(table * 8) + 1.0) / math.log2(8)
+    h = F.relu(F.linear(table.reshape(-1, 2), sd[pre + "cpb_mlp.0.weight"], sd[pre + "cpb_mlp.0.bias"]))
+    bias_table = F.linear(h, sd[pre + "cpb_mlp.2.weight"])  # [(2wh-1)(2ww-1), H]
+    cy, cx = torch.meshgrid(torch.arange(wh), torch.arange(ww), indexing="ij")
+    coords = torch.stack((cy.flatten(), cx.flatten()))
+    rel = coords[:, :, None] - coords[:, None, :]
+    idx = (rel[0] + wh - 1) * (2 * ww - 1) + (rel[1] + ww - 1)
+    area = wh * ww
+    bias = 16 * torch.sigmoid(bias_table[idx.reshape(-1)])
+    return bias.reshape(area, area, -1).permute(2, 0, 1).contiguous()  # [H, A, A]
+
+
+def swin_block(sd: dict, pre: str, x: torch.Tensor, grid_hw, heads: int, target_win, pretrained_window, is_shift_block):
+    """SwinTransformerBlock.forward (post-norm) - v31_swinv2/image_encoder_model.py:213-225 and
+    WindowAttentionWithRelPos - components/windowed_attention.py:65-123"""
+    B, N, C = x.shape
+    gh, gw = grid_hw
+    (wh, ww), (sh, sw) = swin_window_and_shift(grid_hw, target_win)
+    need_shift = is_shift_block and (sh > 0 or sw > 0)
+    img = x.reshape(B, gh, gw, C)
+    if need_shift:
+        img = torch.roll(img, shifts=(-sh, -sw), dims=(1, 2))
+    nwy, nwx = gh // wh, gw // ww
+    win = img.reshape(B, nwy, wh, nwx, ww, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, wh * ww, C)
+    P, A, _ = win.shape
+    d = C // heads
+    a = pre + "attn."
+    qkv = F.linear(win, sd[a + "qkv.weight"]).reshape(P, A, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.unbind(0)
+    q = q + sd[a + "q_bias"].reshape(1, heads, 1, d)
+    v = v + sd[a + "v_bias"].reshape(1, heads, 1, d)
+    att = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)
+    # logit_scale is clamped (<= ln 100) and exponentiated at load time (convert_midas_state_dict_keys.py:115-131)
+    att = att * torch.clamp(sd[a + "logit_scale"], max=math.log(100.0)).exp()
+    att = att + swin_cpb_bias(sd, a, (wh, ww), pretrained_window).unsqueeze(0)
+    if need_shift:
+        mask = swin_shift_mask(grid_hw, (wh, ww), (sh, sw))
+        att = att + mask.unsqueeze(1).repeat(B, 1, 1, 1)
+    o = (att.softmax(dim=-1) @ v).transpose(1, 2).reshape(P, A, C)
+    o = F.linear(o, sd[a + "proj.weight"], sd[a + "proj.bias"])
+    img = o.reshape(B, nwy, nwx, wh, ww, C).permute(0, 1, 3, 2, 4, 5).reshape(B, gh, gw, C)
+    if need_shift:
+        img = torch.roll(img, shifts=(sh, sw), dims=(1, 2))
+    t = img.reshape(B, N, C)
+    x = x + F.layer_norm(t, (C,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5)
+    m = F.linear(F.gelu(F.linear(x, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])),
+                 sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    return x + F.layer_norm(m, (C,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
+
+
+def swin_patch_merge(sd: dict, s: int, x: torch.Tensor, grid_hw):
+    """PatchMerge.forward - v31_swinv2/components/patch_merge.py:49-103 (concat order TL, BL, TR, BR)"""
+    B, N, C = x.shape
+    gh, gw = grid_hw
+    img = x.reshape(B, gh, gw, C)
+    cat = torch.cat([img[:, 0::2, 0::2], img[:, 1::2, 0::2], img[:, 0::2, 1::2], img[:, 1::2, 1::2]], dim=-1)
+    t = F.linear(cat.reshape(B, N // 4, 4 * C), sd[f"pretrained.model.layers.{s}.downsample.reduction.weight"])
+    p = f"pretrained.model.layers.{s}.downsample.norm."
+    return F.layer_norm(t, (t.shape[-1],), sd[p + "weight"], sd[p + "bias"], 1e-5), (gh // 2, gw // 2)
+
+
+def forward_swinv2(sd: dict, img_bchw: torch.Tensor, cfg: dict | None = None, return_stages: bool = False):
+    """DPTModel.forward with the SwinV2 sub-models (make_swinv2_dpt.py:61-139)"""
+    cfg = cfg or infer_config_swinv2(sd)
+    with torch.inference_mode():
+        w, b = sd["pretrained.model.patch_embed.proj.weight"], sd["pretrained.model.patch_embed.proj.bias"]
+        x = F.conv2d(img_bchw, w, b, stride=w.shape[-1])  # v31_swinv2/patch_embed.py:76-94 (conv + LayerNorm)
+        grid_hw = tuple(x.shape[2:])
+        x = x.flatten(2).transpose(1, 2)
+        tokens = F.layer_norm(x, (x.shape[-1],), sd["pretrained.model.patch_embed.norm.weight"],
+                              sd["pretrained.model.patch_embed.norm.bias"], 1e-5)
+        taps, g, x = [], grid_hw, tokens
+        for s in range(4):
+            if s > 0:
+                x, g = swin_patch_merge(sd, s - 1, x, g)
+            for bi in range(cfg["layers_per_stage"][s]):
+                x = swin_block(sd, f"pretrained.model.layers.{s}.blocks.{bi}.", x, g, cfg["heads_per_stage"][s],
+                               cfg["window_size_hw"], cfg["pretrained_window_sizes_per_stage"][s], bi % 2 == 1)
+            taps.append(x)
+        maps = []
+        for k, t in enumerate(taps):  # ReassembleBlock - v31_swinv2/reassembly_model.py:113-122
+            gk = (grid_hw[0] // 2**k, grid_hw[1] // 2**k)
+            maps.append(F.conv2d(t.transpose(1, 2).unflatten(2, gk), sd[f"scratch.layer{k + 1}_rn.weight"], None, padding=1))
+        fused = _midas_fusion(sd, *maps)
+        depth = _midas_head(sd, fused)
+    if return_stages:
+        return {"tokens": tokens, "taps": tuple(taps), "maps": tuple(maps), "fused": fused, "depth": depth, "grid_hw": grid_hw}
+    return depth
+
+
+SWINV2_CONFIGS = {
+    # make_swinv2_dpt.py docstring
+    "swinv2_large_384": dict(F0=192, heads=(6, 12, 24, 48), layers=(2, 2, 18, 2), base=96, win=24, C=256),
+    "swinv2_base_384": dict(F0=128, heads=(4, 8, 16, 32), layers=(2, 2, 18, 2), base=96, win=24, C=256),
+    "swinv2_tiny_256": dict(F0=96, heads=(3, 6, 12, 24), layers=(2, 2, 6, 2), base=64, win=16, C=256),
+    "swinv2_micro": dict(F0=32, heads=(1, 2, 4, 8), layers=(2, 2, 2, 2), base=32, win=8, C=32),
+}
+
+
+def make_synthetic_state_dict_swinv2(name: str = "swinv2_micro", seed: int = 0) -> dict:
+    """MiDaS v3.1 SwinV2 key schema"""
+    cfg = SWINV2_CONFIGS[name]
+    F0, Hs, Ls, base, win, C = cfg["F0"], cfg["heads"], cfg["layers"], cfg["base"], cfg["win"], cfg["C"]
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    def fan(*shape):
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        return rn(*shape, std=fan_in**-0.5)
+
+    sd = {}
+    sd["pretrained.model.patch_embed.proj.weight"] = fan(F0, 3, 4, 4)
+    sd["pretrained.model.patch_embed.proj.bias"] = rn(F0, std=0.1)
+    sd["pretrained.model.patch_embed.norm.weight"] = 1.0 + rn(F0, std=0.1)
+    sd["pretrained.model.patch_embed.norm.bias"] = rn(F0, std=0.1)
+    for s in range(4):
+        Fs, H = F0 * 2**s, Hs[s]
+        grid = base // 2**s
+        for bi in range(Ls[s]):
+            p = f"pretrained.model.layers.{s}.blocks.{bi}."
+            sd[p + "attn.logit_scale"] = math.log(10.0) + rn(H, 1, 1, std=1.5)  # some above ln 100 -> exercises the clamp
+            sd[p + "attn.q_bias"] = rn(Fs, std=0.3)
+            sd[p + "attn.v_bias"] = rn(Fs, std=0.3)
+            sd[p + "attn.qkv.weight"] = fan(3 * Fs, Fs) * 1.5
+            sd[p + "attn.cpb_mlp.0.weight"] = rn(512, 2, std=1.0)
+            sd[p + "attn.cpb_mlp.0.bias"] = rn(512, std=0.5)
+            sd[p + "attn.cpb_mlp.2.weight"] = rn(H, 512, std=0.08)
+            sd[p + "attn.proj.weight"] = fan(Fs, Fs)
+            sd[p + "attn.proj.bias"] = rn(Fs, std=0.1)
+            for nrm in ("norm1", "norm2"):
+                sd[p + nrm + ".weight"] = 0.5 + rn(Fs, std=0.1)
+                sd[p + nrm + ".bias"] = rn(Fs, std=0.1)
+            sd[p + "mlp.fc1.weight"] = fan(4 * Fs, Fs)
+            sd[p + "mlp.fc1.bias"] = rn(4 * Fs, std=0.1)
+            sd[p + "mlp.fc2.weight"] = fan(Fs, 4 * Fs)
+            sd[p + "mlp.fc2.bias"] = rn(Fs, std=0.1)
+            w = min(win, grid)
+            if bi % 2 == 1 and grid > w:  # the stored masks are dropped by the loader but drive config inference
+                sd[p + "attn_mask"] = torch.zeros((grid // w) ** 2, w * w, w * w)
+        if s < 3:
+            p = f"pretrained.model.layers.{s}.downsample."
+            sd[p + "reduction.weight"] = fan(2 * Fs, 4 * Fs)
+            sd[p + "norm.weight"] = 1.0 + rn(2 * Fs, std=0.1)
+            sd[p + "norm.bias"] = rn(2 * Fs, std=0.1)
+    for k in range(4):
+        sd[f"scratch.layer{k + 1}_rn.weight"] = fan(C, F0 * 2**k, 3, 3)
+    for i in (1, 2, 3, 4):
+        for u in (1, 2):
+            for cv in (1, 2):
+                p = f"scratch.refinenet{i}.resConfUnit{u}.conv{cv}."
+                sd[p + "weight"] = fan(C, C, 3, 3) * (1.4 if cv == 1 else 0.7)
+                sd[p + "bias"] = rn(C, std=0.1)
+        sd[f"scratch.refinenet{i}.out_conv.weight"] = fan(C, C, 1, 1)
+        sd[f"scratch.refinenet{i}.out_conv.bias"] = rn(C, std=0.1)
+    sd["scratch.output_conv.0.weight"] = fan(C // 2, C, 3, 3)
+    sd["scratch.output_conv.0.bias"] = rn(C // 2, std=0.1)
+    sd["scratch.output_conv.2.weight"] = fan(32, C // 2, 3, 3) * 1.4
+    sd["scratch.output_conv.2.bias"] = rn(32, std=0.1) + 0.2
+    sd["scratch.output_conv.4.weight"] = fan(1, 32, 1, 1)
+    sd["scratch.output_conv.4.bias"] = torch.full((1,), 2.0)
+    return sd

@@ -119,6 +119,23 @@ def main():
         print(f"beit_tiny_{tag}: depth std {ref['depth'].std().item():.4f} mean {ref['depth'].mean().item():.4f}; "
               f"taps std {[round(t.std().item(), 3) for t in ref['taps']]}")
 
+    # ---- MiDaS v3.1 SwinV2 (micro synthetic config: window 8, 4 stages x 2 blocks; b is non-square -> 8x10 windows)
+    for tag, (B, H, W) in {"a": (2, 128, 128), "b": (1, 128, 160)}.items():
+        sd = O.make_synthetic_state_dict_swinv2("swinv2_micro", seed=4)
+        img = O.make_input(B, H, W, seed=3)
+        cfg, ref = run_reference(sd, img, enable_optimizations=True)
+        fix = {
+            "model_type": "swinv2",
+            "config": {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in cfg.items()},
+            "sd_seed": 4, "sd_name": "swinv2_micro", "sd_checksum": state_dict_checksum(sd),
+            "img": img,
+            "tokens": ref["tokens"], "taps": list(ref["taps"]), "maps": list(ref["maps"]),
+            "fused": ref["fused"], "depth": ref["depth"], "grid_hw": ref["grid_hw"],
+        }
+        torch.save(fix, os.path.join(out_dir, f"swinv2_micro_{tag}.pt"))
+        print(f"swinv2_micro_{tag}: depth std {ref['depth'].std().item():.4f} mean {ref['depth'].mean().item():.4f}; "
+              f"taps std {[round(t.std().item(), 3) for t in ref['taps']]}")
+
     # ---- oracle vs reference, right here
     for name in sorted(os.listdir(out_dir)):
         if not name.endswith(".pt"):
@@ -127,6 +144,9 @@ def main():
         if fix.get("model_type") == "beit":
             sd = O.make_synthetic_state_dict_beit(fix["sd_name"], fix["sd_seed"])
             st = O.forward_beit(sd, fix["img"], return_stages=True)
+        elif fix.get("model_type") == "swinv2":
+            sd = O.make_synthetic_state_dict_swinv2(fix["sd_name"], fix["sd_seed"])
+            st = O.forward_swinv2(sd, fix["img"], return_stages=True)
         else:
             sd = fix.get("state_dict") or O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"])
             st = O.forward(sd, fix["img"], return_stages=True)
