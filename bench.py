@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--model", default="vitl",
-                    choices=["vitl", "vitb", "vits", "tiny", "beit_large_384", "beit_base_384", "beit_tiny"])
+                    choices=["vitl", "vitb", "vits", "tiny", "beit_large_384", "beit_base_384", "beit_tiny",
+                             "swinv2_large_384", "swinv2_base_384", "swinv2_tiny_256", "swinv2_micro"])
     ap.add_argument("--batch", type=int, default=32, help="global batch (frames per step)")
     ap.add_argument("--size", type=int, default=504)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
@@ -66,7 +67,7 @@ def load_peaks():
 def algorithmic_gflop_per_frame(model, size):
     """BASELINE.md section 3 (torch flop counter on the reference modules, 2*MAC, matmul/conv only)."""
     table = {("vits", 504): 107.32, ("vitb", 504): 356.69, ("vitl", 504): 1224.94, ("vitl", 532): 1385.8,
-             ("beit_large_384", 384): 516.41}
+             ("beit_large_384", 384): 516.41, ("swinv2_large_384", 384): 343.73}
     return table.get((model, size))
 
 
@@ -126,12 +127,16 @@ def _oracle_model(O, model_name):
     """(synthetic upstream-format checkpoint, oracle forward) for a model name"""
     if model_name.startswith("beit"):
         return O.make_synthetic_state_dict_beit(model_name, seed=11), O.forward_beit
+    if model_name.startswith("swinv2"):
+        return O.make_synthetic_state_dict_swinv2(model_name, seed=11), O.forward_swinv2
     return O.make_synthetic_state_dict(model_name, seed=11), O.forward
 
 
 def _checkpoint_file_name(model_name):
     # the reference sniffs Depth-Anything v1/v2 from the FILE NAME (make_dpt.py:98-104)
-    return f"dpt_{model_name}_synthetic.pt" if model_name.startswith("beit") else f"depth_anything_v2_{model_name}_synthetic.pth"
+    if model_name.startswith(("beit", "swinv2")):
+        return f"dpt_{model_name}_synthetic.pt"
+    return f"depth_anything_v2_{model_name}_synthetic.pth"
 
 
 def time_cpu_oracle(model_name, size, frames, threads=None):
@@ -363,7 +368,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
-                "workload": (f"MiDaS v3.1 {args.model}" if args.model.startswith("beit") else f"Depth-Anything-V2 {args.model}")
+                "workload": (f"MiDaS v3.1 {args.model}" if args.model.startswith(("beit", "swinv2")) else f"Depth-Anything-V2 {args.model}")
                             + f" (synthetic seeded weights), global batch {b_global}, 3x{S}x{S}"
                             + (" (reference's effective 518 setting)" if S == 504 else "") + f", {args.dtype}",
                 "global_batch": b_global, "per_gpu_batch": b_local, "parallelism": f"dp{world} batch-shard + all-gather",

@@ -49,7 +49,12 @@ typedef struct dpt_config {
   int patch_size_px;       /* 14 (DINOv2) or 16 (BEiT) */
   int base_grid_h, base_grid_w;
   int is_metric;           /* sigmoid instead of the final ReLU (head_model.py:84) */
-  float ln_eps;            /* 1e-6 (misc_helpers.py:202) */
+  float ln_eps;            /* 1e-6 (misc_helpers.py:202); 1e-5 for SwinV2 */
+  /* SwinV2 only (make_swinv2_dpt.py:61-72): features_per_token = stage-0 width, stage s has width << s */
+  int heads_per_stage[4];
+  int layers_per_stage[4];
+  int window_h, window_w;
+  int pretrained_window[4]; /* 0 = none */
 } dpt_config;
 
 /* lifetime ---------------------------------------------------------------------------------------------------- */
@@ -79,7 +84,8 @@ int dpt_forward_host(dpt_handle h, const void* host_img_bchw, void* host_depth_b
 /* PatchEmbed.forward (v2_depthanything/patch_embed.py:77-99): img -> tokens [B, gh*gw, F] 16-bit */
 int dpt_patch_embed(dpt_handle h, const void* img_bchw, void* tokens, void* workspace, size_t workspace_bytes, int B,
                     int H, int W, void* stream);
-/* DinoV2Model4Stages.forward (image_encoder_model.py:80-94): tokens -> four taps [B, 1+gh*gw, F] 16-bit */
+/* DinoV2Model4Stages.forward (image_encoder_model.py:80-94): tokens -> four taps [B, 1+gh*gw, F] 16-bit
+ * (SwinV2: SwinV2Model4Stages.forward, taps [B, (gh>>s)*(gw>>s), F<<s], no cls token) */
 int dpt_encoder(dpt_handle h, const void* tokens, void* const taps[4], void* workspace, size_t workspace_bytes, int B,
                 int gh, int gw, void* stream);
 /* ReassembleModel.forward (reassembly_model.py:61-94): taps -> maps [B,4g,4g,C] [B,2g,2g,C] [B,g,g,C] [B,g/2,g/2,C] */
@@ -99,10 +105,11 @@ int dpt_head(dpt_handle h, const void* fused, void* depth, void* workspace, size
 int dpt_op_conv_gemm(const void* A, const void* Wt, const float* bias, void* out, const void* add1, const void* add2,
                      void* out_relu, int B, int H, int W, int C, int N, int taps, int xoff, int act, int out_f32,
                      int dtype, void* stream);
-/* O = softmax(scale * Q K^T + bias) V, qkv [B,N,3F] 16-bit (F = heads*64), out [B,N,F]; bias [heads,N,bias_ld]
- * 16-bit with bias_ld a multiple of 128 (>= N), or NULL */
-int dpt_op_attention(const void* qkv, const void* bias, int64_t bias_ld, void* out, int B, int N, int heads,
-                     float scale, int dtype, void* stream);
+/* O = softmax(scale * Q K^T + bias) V, qkv [B,N,3F] 16-bit (F = heads*head_dim, head_dim 64 or 32), out [B,N,F];
+ * bias [bias_wmod, heads, N, bias_ld] 16-bit with bias_ld a multiple of 128 (>= N), table (b % bias_wmod) is used
+ * for batch entry b; or NULL */
+int dpt_op_attention(const void* qkv, const void* bias, int64_t bias_ld, int bias_wmod, void* out, int B, int N,
+                     int heads, int head_dim, float scale, int dtype, void* stream);
 /* y = LayerNorm(x) * w + b, x [M,F] f32, y [M,F] 16-bit */
 int dpt_op_layernorm(const float* x, const float* w, const float* b, void* y, int64_t M, int F, float eps, int dtype,
                      void* stream);

@@ -31,6 +31,11 @@ class DptConfig(C.Structure):
         ("base_grid_w", C.c_int),
         ("is_metric", C.c_int),
         ("ln_eps", C.c_float),
+        ("heads_per_stage", C.c_int * 4),
+        ("layers_per_stage", C.c_int * 4),
+        ("window_h", C.c_int),
+        ("window_w", C.c_int),
+        ("pretrained_window", C.c_int * 4),
     ]
 
 
@@ -58,7 +63,7 @@ SYMBOLS = [
     ("dpt_fusion", _I, [_VP, _PP4, _VP, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_head", _I, [_VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_op_conv_gemm", _I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
-    ("dpt_op_attention", _I, [_VP, _VP, C.c_int64, _VP, _I, _I, _I, _F, _I, _VP]),
+    ("dpt_op_attention", _I, [_VP, _VP, C.c_int64, _I, _VP, _I, _I, _I, _I, _F, _I, _VP]),
     ("dpt_op_layernorm", _I, [_VP, _VP, _VP, _VP, C.c_int64, _I, _F, _I, _VP]),
     ("dpt_op_resize_bilinear", _I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     ("dpt_op_last_error", C.c_char_p, []),

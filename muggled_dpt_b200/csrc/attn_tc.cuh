@@ -45,6 +45,7 @@ struct __align__(64) AttnParams {
   void* out;          // [B, N, F] 16-bit
   const void* bias;   // optional additive bias [H, N, ldb] 16-bit (BEiT relative position bias), shared over batch
   long long ldb;      // row stride of bias in elements: a multiple of 128 (whole kv tiles stay in bounds)
+  int bias_wmod;      // bias table index = (batch % bias_wmod) * H + h  (SwinV2: per-window shift masks; else 1)
 };
 
 // 32 consecutive 16-bit bias values (64 B, 16-byte aligned) -> fp32, pre-multiplied by log2(e)
@@ -83,7 +84,10 @@ __device__ __noinline__ void rescale_accumulator(uint32_t o_addr, float beta) {
   tc_fence_before();
 }
 
-template <bool HAS_BIAS, bool BF16>
+// HD = features per head: 64 (ViT / BEiT) or 32 (SwinV2). For HD = 32 the 64-column TMA boxes start at the head's
+// first column, so the head occupies the first half of every tile: QK^T contracts over K = 32 only, P@V still runs at
+// N = 64 and the upper 32 accumulator columns are ignored.
+template <bool HAS_BIAS, bool BF16, int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -148,16 +152,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &p.tmQKV, q_full, h * ATT_D, q0, b);
+      tma_load_3d(sQ, &p.tmQKV, q_full, h * HD, q0, b);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sK + s * ATT_TILE_BYTES, &p.tmQKV, &k_full[s], p.F + h * ATT_D, j * ATT_BN, b);
+        tma_load_3d(sK + s * ATT_TILE_BYTES, &p.tmQKV, &k_full[s], p.F + h * HD, j * ATT_BN, b);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sV + s * ATT_TILE_BYTES, &p.tmQKV, &v_full[s], 2 * p.F + h * ATT_D, j * ATT_BN, b);
+        tma_load_3d(sV + s * ATT_TILE_BYTES, &p.tmQKV, &v_full[s], 2 * p.F + h * HD, j * ATT_BN, b);
       }
     }
     __syncwarp();
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       {
         const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
         umma_commit(&k_empty[0]);
         umma_commit(s_full);
       }
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
           tc_fence_after();
           const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK + s1 * ATT_TILE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
           umma_commit(&k_empty[s1]);
           umma_commit(s_full);
         }
@@ -230,7 +234,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     const uint16_t* bias_row = nullptr;
     if constexpr (HAS_BIAS) {
       // rows past N read row N-1 (never stored); ldb is a multiple of ATT_BN so whole kv tiles are in bounds
-      bias_row = reinterpret_cast<const uint16_t*>(p.bias) + ((long long)h * p.N + min(qrow, p.N - 1)) * p.ldb;
+      bias_row = reinterpret_cast<const uint16_t*>(p.bias) +
+                 (((long long)(b % p.bias_wmod) * p.H + h) * p.N + min(qrow, p.N - 1)) * p.ldb;
     }
     const uint32_t s_addr = tmem_S + lane_addr;
     const uint32_t o_addr = tmem_O + lane_addr;
@@ -343,9 +348,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       tmem_ld_wait_dep(ov[0]);
       tmem_ld_wait_dep(ov[1]);
       if (qrow < p.N) {
-        uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)b * p.N + qrow) * p.F + h * ATT_D;
+        uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)b * p.N + qrow) * p.F + h * HD;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
+        for (int ch = 0; ch < HD / 8; ++ch) {
           const uint32_t* w = &ov[ch >> 2][(ch & 3) * 8];
           uint4 o;
           o.x = pack2(__uint_as_float(w[0]) * inv_l, __uint_as_float(w[1]) * inv_l, is_bf16);

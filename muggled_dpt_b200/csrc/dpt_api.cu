@@ -17,6 +17,7 @@
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_misc.cuh"
+#include "kernels_swin.cuh"
 
 using namespace dpt;
 
@@ -303,31 +304,33 @@ bool add_gemm(Ctx& c, GemmOp op) {
   return true;
 }
 
-template <bool HAS_BIAS, bool BF16>
+template <bool HAS_BIAS, bool BF16, int HD>
 cudaError_t launch_attn_inst(const AttnParams& p, dim3 grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<HAS_BIAS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ATT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<HAS_BIAS, BF16, HD>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  attn_tc_kernel<HAS_BIAS, BF16><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
+  attn_tc_kernel<HAS_BIAS, BF16, HD><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
   return cudaGetLastError();
 }
-template <bool HAS_BIAS>
+template <bool HAS_BIAS, int HD>
 cudaError_t launch_attn(const AttnParams& p, dim3 grid, cudaStream_t s) {
-  return p.is_bf16 ? launch_attn_inst<HAS_BIAS, true>(p, grid, s) : launch_attn_inst<HAS_BIAS, false>(p, grid, s);
+  return p.is_bf16 ? launch_attn_inst<HAS_BIAS, true, HD>(p, grid, s) : launch_attn_inst<HAS_BIAS, false, HD>(p, grid, s);
 }
 
-// bias (optional): [heads, N, ldb] 16-bit with ldb a multiple of 128
-bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, void* out, int B, int N, int heads,
-                   float scale) {
+// qkv [B, N, 3F] with F = heads * hd (hd = 64 or 32); bias (optional): [wmod, heads, N, ldb] 16-bit, ldb % 128 == 0
+bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, int wmod, void* out, int B, int N,
+                   int heads, int hd, float scale) {
+  if (hd != 64 && hd != 32) return c.fail("attention: head_dim must be 64 or 32");
   if (bias != nullptr && (ldb % ATT_BN != 0 || ldb < N)) return c.fail("attention: bias row stride must be a multiple of 128");
-  if (c.dry) return true;
+  if (c.dry) return true;  // (workspace sizing pass: buffers are null)
+  if (hd == 32 && bias == nullptr) return c.fail("attention: the head_dim 32 kernel is built with bias only (SwinV2)");
   AttnParams p;
   memset(&p, 0, sizeof p);
-  const int F = heads * 64;
+  const int F = heads * hd;
   uint64_t dims[3] = {(uint64_t)3 * F, (uint64_t)N, (uint64_t)B};
   uint64_t str[2] = {(uint64_t)3 * F * 2, (uint64_t)3 * F * 2 * N};
   uint32_t box[3] = {64, 128, 1};
@@ -338,11 +341,13 @@ bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, voi
   p.out = out;
   p.bias = bias;
   p.ldb = ldb;
+  p.bias_wmod = wmod > 0 ? wmod : 1;
   dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
   const bool has_bias = bias != nullptr;
-  c.add("attn:" + c.scope, 4.0 * B * heads * (double)N * N * 64.0, 4.0 * (double)B * N * F * 2.0,
-        [p, grid, has_bias](cudaStream_t s) {
-          return has_bias ? launch_attn<true>(p, grid, s) : launch_attn<false>(p, grid, s);
+  c.add("attn:" + c.scope, 4.0 * B * heads * (double)N * N * hd, 4.0 * (double)B * N * F * 2.0,
+        [p, grid, has_bias, hd](cudaStream_t s) {
+          if (hd == 32) return launch_attn<true, 32>(p, grid, s);
+          return has_bias ? launch_attn<true, 64>(p, grid, s) : launch_attn<false, 64>(p, grid, s);
         });
   return true;
 }
@@ -367,6 +372,32 @@ bool add_layernorm(Ctx& c, const float* x, const float* w, const float* b, void*
     const int rows_per_block = 8;
     const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
     DISPATCH_T(is_bf16, (layernorm_kernel<T, float><<<grid, rows_per_block * 32, 0, s>>>(x, w, b, (T*)y, M, F, eps)));
+    return cudaGetLastError();
+  });
+  return true;
+}
+
+// LayerNorm on 16-bit input (SwinV2 patch embed: conv -> LayerNorm, v31_swinv2/patch_embed.py:59,92)
+bool add_layernorm_h(Ctx& c, const void* x16, const float* w, const float* b, void* y, long long M, int F, float eps) {
+  if (F % 4 != 0 || F > 1536) return c.fail("layernorm: F must be a multiple of 4 and <= 1536");
+  if (c.dry) return true;
+  const int is_bf16 = c.is_bf16;
+  c.add("layernorm:" + c.scope, 0.0, (double)M * F * 4.0, [=](cudaStream_t s) {
+    const int rows_per_block = 8;
+    const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+    DISPATCH_T(is_bf16, (layernorm_kernel<T, T><<<grid, rows_per_block * 32, 0, s>>>((const T*)x16, w, b, (T*)y, M, F, eps)));
+    return cudaGetLastError();
+  });
+  return true;
+}
+
+bool add_cast_to_half(Ctx& c, const float* x, void* y, long long n, const char* label) {
+  if (n % 4 != 0) return c.fail("cast: size must be a multiple of 4");
+  if (c.dry) return true;
+  const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+  c.add(std::string(label) + ":" + c.scope, 0.0, (double)n * 6.0, [=](cudaStream_t s) {
+    const int grid = ew_grid(n / 4, 256, nsm);
+    DISPATCH_T(is_bf16, (cast_f32_kernel<T><<<grid, 256, 0, s>>>(x, (T*)y, n / 4)));
     return cudaGetLastError();
   });
   return true;
@@ -444,10 +475,21 @@ bool build_patch_embed(Ctx& c, const void* img, void* tokens, int B, int H, int 
   op.A = A; op.B = 1; op.Ht = 1; op.Wt = (int)M; op.C = kpad;
   op.Wt_ptr = w->ptr; op.N = F; op.taps = 1; op.kpad = kpad;
   op.bias = (const float*)b->ptr;
-  op.out = tokens;
   op.label = "patch_embed";
   c.scope = "";
-  bool ok = add_gemm(c, op);
+  bool ok;
+  if (cfg.variant == DPT_VARIANT_SWINV2) {
+    const Weight *lw = get_w(c, "patch.ln.w", DPT_F32), *lb = get_w(c, "patch.ln.b", DPT_F32);
+    if (!lw || !lb) return false;
+    void* tmp = c.ar.alloc((size_t)M * F * 2);
+    op.out = tmp;
+    ok = add_gemm(c, op);
+    c.scope = "patch_embed";
+    ok = ok && add_layernorm_h(c, tmp, (const float*)lw->ptr, (const float*)lb->ptr, tokens, M, F, cfg.ln_eps);
+  } else {
+    op.out = tokens;
+    ok = add_gemm(c, op);
+  }
   c.ar.reset(mk);
   return ok;
 }
@@ -544,9 +586,9 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
           return cudaGetLastError();
         });
       }
-      add_attention(c, qkv, bias_buf, ldb, att, B, N, heads, scale);
+      add_attention(c, qkv, bias_buf, ldb, 1, att, B, N, heads, 64, scale);
     } else {
-      add_attention(c, qkv, nullptr, 0, att, B, N, heads, scale);
+      add_attention(c, qkv, nullptr, 0, 1, att, B, N, heads, 64, scale);
     }
     {
       GemmOp op;  // x += (gamma1 . proj)(att)   (LayerScale folded into the packed weights)
@@ -584,6 +626,235 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     }
   }
   c.ar.reset(mk);
+  return c.ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SwinV2 (v31_swinv2/*)
+
+// adjust_window_and_shift_sizes - v31_swinv2/components/windowed_attention.py:345-388 (one axis)
+void swin_window_and_shift(int patch, int targ, int& win, int& shift) {
+  win = std::min(targ, patch);
+  if (patch % win != 0) {
+    int best = -1;
+    for (int d = win / 2; d < 2 * win; ++d)
+      if (d > 0 && patch % d == 0 && (best < 0 || std::abs(patch - d) < std::abs(patch - best))) best = d;
+    win = best;
+  }
+  shift = patch <= win ? 0 : win / 2;
+}
+
+// Python slice semantics of make_shift_mask's h_slices / w_slices (windowed_attention.py:420-421)
+void swin_mask_slices_axis(int n, int win, int shift, int* s0, int* s1) {
+  s0[0] = 0;                          s1[0] = n - win;                  // slice(0, -win)
+  s0[1] = n - win;                    s1[1] = shift > 0 ? n - shift : 0;  // slice(-win, -shift): -0 == 0 -> empty
+  s0[2] = shift > 0 ? n - shift : 0;  s1[2] = n;                        // slice(-shift, None): -0 == 0 -> everything
+}
+
+// SwinV2Model4Stages.forward - v31_swinv2/image_encoder_model.py:77-98,164-169,213-225
+bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, int gh, int gw) {
+  const dpt_config& cfg = c.m->cfg;
+  const int hd = half_dt(c);
+  const int F0 = cfg.features_per_token;
+  if (gh % 8 || gw % 8) return c.fail("SwinV2 needs a patch grid divisible by 8 (image multiple of 32 px)");
+  const size_t mk = c.ar.mark();
+  const long long M0 = (long long)B * gh * gw;
+  float* x = (float*)c.ar.alloc((size_t)M0 * F0 * 4);
+  float* x_next = (float*)c.ar.alloc((size_t)M0 * F0 * 2);  // next stage: N/4 tokens, 2F features
+  void* xw = c.ar.alloc((size_t)M0 * F0 * 2);
+  void* qkv = c.ar.alloc((size_t)M0 * 3 * F0 * 2);
+  void* att = c.ar.alloc((size_t)M0 * F0 * 2);
+  void* y = c.ar.alloc((size_t)M0 * F0 * 2);
+  void* hid = c.ar.alloc((size_t)M0 * 4 * F0 * 2);
+  if (!c.dry) {
+    const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+    const long long n = M0 * F0;
+    c.add("cast_tokens", 0.0, (double)n * 6.0, [=](cudaStream_t s) {
+      const int grid = ew_grid(n / 4, 256, nsm);
+      DISPATCH_T(is_bf16, (cast_to_f32_kernel<T><<<grid, 256, 0, s>>>((const T*)tokens, x, n / 4)));
+      return cudaGetLastError();
+    });
+  }
+  int sgh = gh, sgw = gw;
+  for (int st = 0; st < 4 && c.ok; ++st) {
+    const int F = F0 << st, heads = cfg.heads_per_stage[st];
+    if (heads * 32 != F) return c.fail("SwinV2 stages must have 32 features per head");
+    const std::string sp = "sw" + std::to_string(st) + ".";
+    if (st > 0) {
+      // PatchMerge (components/patch_merge.py:49-103): 2x2 gather -> Linear(4C, 2C, no bias) -> LayerNorm
+      const std::string mp = "sw" + std::to_string(st - 1) + ".merge.";
+      const Weight *mw = get_w(c, mp + "w", hd), *lw = get_w(c, mp + "ln.w", DPT_F32), *lb = get_w(c, mp + "ln.b", DPT_F32);
+      if (!c.ok) return false;
+      const int Cp = F / 2, pgh = sgh * 2, pgw = sgw * 2;
+      const long long Mn = (long long)B * sgh * sgw;
+      c.scope = mp;
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+        const float* xin = x;
+        void* mg = hid;
+        c.add("patch_merge_gather:" + mp, 0.0, (double)Mn * 4 * Cp * 6.0, [=](cudaStream_t s) {
+          const int grid = ew_grid(Mn * 4 * (Cp / 4), 256, nsm);
+          DISPATCH_T(is_bf16, (swin_patch_merge_gather_kernel<T><<<grid, 256, 0, s>>>(xin, (T*)mg, B, pgh, pgw, Cp)));
+          return cudaGetLastError();
+        });
+      }
+      GemmOp op;
+      op.A = hid; op.Wt = (int)Mn; op.C = 4 * Cp; op.Wt_ptr = mw->ptr; op.N = F; op.kpad = (int)mw->shape[1];
+      op.out = y; op.label = "reduction";
+      add_gemm(c, op);
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16;
+        const float *lwp = (const float*)lw->ptr, *lbp = (const float*)lb->ptr;
+        float* xo = x_next;
+        const void* yin = y;
+        const float eps = cfg.ln_eps;
+        c.add("ln_merge:" + mp, 0.0, (double)Mn * F * 6.0, [=](cudaStream_t s) {
+          const unsigned grid = (unsigned)((Mn + 7) / 8);
+          SwinWin w0{};
+          DISPATCH_T(is_bf16, (swin_ln_residual_kernel<T, 0, false><<<grid, 256, 0, s>>>((const T*)yin, lwp, lbp, xo, Mn, F, eps, w0)));
+          return cudaGetLastError();
+        });
+      }
+      std::swap(x, x_next);
+    }
+    const long long M = (long long)B * sgh * sgw;
+    int wh, ww, sh, sw;
+    swin_window_and_shift(sgh, cfg.window_h, wh, sh);
+    swin_window_and_shift(sgw, cfg.window_w, ww, sw);
+    const int A = wh * ww, nW = (sgh / wh) * (sgw / ww);
+    const long long ldb = (A + ATT_BN - 1) / ATT_BN * ATT_BN;
+    const size_t mk_stage = c.ar.mark();
+    float* table = (float*)c.ar.alloc((size_t)(2 * wh - 1) * (2 * ww - 1) * heads * 4);
+    void* bias = c.ar.alloc((size_t)nW * heads * A * ldb * 2);
+    const int pre_w = cfg.pretrained_window[st];
+    const float div_h = (float)std::max((pre_w > 0 ? pre_w : wh) - 1, 1), div_w = (float)std::max((pre_w > 0 ? pre_w : ww) - 1, 1);
+    for (int bi = 0; bi < cfg.layers_per_stage[st] && c.ok; ++bi) {
+      const std::string pre = sp + std::to_string(bi) + ".";
+      c.scope = pre;
+      const bool shifted = (bi % 2 == 1) && (sh > 0 || sw > 0);
+      const Weight *qw = get_w(c, pre + "qkv.w", hd), *qb = get_w(c, pre + "qkv.b", DPT_F32);
+      const Weight* ls = get_w(c, pre + "logit", DPT_F32);
+      const Weight *c1 = get_w(c, pre + "cpb.w1", DPT_F32), *cb = get_w(c, pre + "cpb.b1", DPT_F32), *c2 = get_w(c, pre + "cpb.w2", DPT_F32);
+      const Weight *pw = get_w(c, pre + "proj.w", hd), *pb = get_w(c, pre + "proj.b", DPT_F32);
+      const Weight *n1w = get_w(c, pre + "ln1.w", DPT_F32), *n1b = get_w(c, pre + "ln1.b", DPT_F32);
+      const Weight *n2w = get_w(c, pre + "ln2.w", DPT_F32), *n2b = get_w(c, pre + "ln2.b", DPT_F32);
+      const Weight *f1w = get_w(c, pre + "fc1.w", hd), *f1b = get_w(c, pre + "fc1.b", DPT_F32);
+      const Weight *f2w = get_w(c, pre + "fc2.w", hd), *f2b = get_w(c, pre + "fc2.b", DPT_F32);
+      if (!c.ok) return false;
+      SwinWin w{sgh, sgw, wh, ww, shifted ? sh : 0, shifted ? sw : 0};
+      SwinMaskSlices ms{};
+      swin_mask_slices_axis(sgh, wh, sh, ms.h0, ms.h1);
+      swin_mask_slices_axis(sgw, ww, sw, ms.w0, ms.w1);
+      const int n_wm = shifted ? nW : 1;
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+        const float* xin = x;
+        const float *w1p = (const float*)c1->ptr, *b1p = (const float*)cb->ptr, *w2p = (const float*)c2->ptr;
+        const int ldbi = (int)ldb, sh_i = shifted ? 1 : 0;
+        c.add("window_gather:" + pre, 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
+          const int grid = ew_grid(M * (F / 4), 256, nsm);
+          DISPATCH_T(is_bf16, (swin_window_gather_kernel<T><<<grid, 256, 0, s>>>(xin, (T*)xw, w, B, F)));
+          return cudaGetLastError();
+        });
+        c.add("cpb_table:" + pre, 0.0, 0.0, [=](cudaStream_t s) {
+          swin_cpb_table_kernel<<<(2 * wh - 1) * (2 * ww - 1), 256, 0, s>>>(w1p, b1p, w2p, table, wh, ww, heads, div_h, div_w);
+          return cudaGetLastError();
+        });
+        c.add("swin_bias:" + pre, 0.0, (double)n_wm * heads * A * ldb * 2.0, [=](cudaStream_t s) {
+          DISPATCH_T(is_bf16, (swin_bias_kernel<T><<<dim3(A, heads, n_wm), 128, 0, s>>>(table, (T*)bias, w, ms, heads, sh_i, ldbi)));
+          return cudaGetLastError();
+        });
+      }
+      {
+        GemmOp op;
+        op.A = xw; op.Wt = (int)M; op.C = F; op.Wt_ptr = qw->ptr; op.N = 3 * F; op.kpad = (int)qw->shape[1];
+        op.bias = (const float*)qb->ptr; op.out = qkv; op.label = "qkv";
+        add_gemm(c, op);
+      }
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16;
+        const float* lsp = (const float*)ls->ptr;
+        c.add("qk_normalize:" + pre, 0.0, (double)M * F * 2.0 * 4.0, [=](cudaStream_t s) {
+          const long long warps = M * heads * 2;
+          const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+          DISPATCH_T(is_bf16, (swin_qk_normalize_kernel<T><<<grid, 256, 0, s>>>((T*)qkv, lsp, M, F, heads)));
+          return cudaGetLastError();
+        });
+      }
+      add_attention(c, qkv, bias, ldb, n_wm, att, B * nW, A, heads, 32, 1.0f);
+      {
+        GemmOp op;
+        op.A = att; op.Wt = (int)M; op.C = F; op.Wt_ptr = pw->ptr; op.N = F; op.kpad = (int)pw->shape[1];
+        op.bias = (const float*)pb->ptr; op.out = y; op.label = "proj";
+        add_gemm(c, op);
+      }
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16;
+        const float *gp = (const float*)n1w->ptr, *bp = (const float*)n1b->ptr;
+        float* xo = x;
+        const void* yin = y;
+        const float eps = cfg.ln_eps;
+        c.add("ln_residual:" + pre + "attn", 0.0, (double)M * F * 10.0, [=](cudaStream_t s) {
+          const unsigned grid = (unsigned)((M + 7) / 8);
+          DISPATCH_T(is_bf16, (swin_ln_residual_kernel<T, 1, true><<<grid, 256, 0, s>>>((const T*)yin, gp, bp, xo, M, F, eps, w)));
+          return cudaGetLastError();
+        });
+      }
+      add_cast_to_half(c, x, xw, M * F, "cast_mlp_in");
+      {
+        GemmOp op;
+        op.A = xw; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = (int)f1w->shape[0]; op.kpad = (int)f1w->shape[1];
+        op.bias = (const float*)f1b->ptr; op.act = ACT_GELU; op.out = hid; op.label = "fc1";
+        add_gemm(c, op);
+      }
+      {
+        GemmOp op;
+        op.A = hid; op.Wt = (int)M; op.C = (int)f1w->shape[0]; op.Wt_ptr = f2w->ptr; op.N = F; op.kpad = (int)f2w->shape[1];
+        op.bias = (const float*)f2b->ptr; op.out = y; op.label = "fc2";
+        add_gemm(c, op);
+      }
+      if (!c.dry) {
+        const int is_bf16 = c.is_bf16;
+        const float *gp = (const float*)n2w->ptr, *bp = (const float*)n2b->ptr;
+        float* xo = x;
+        const void* yin = y;
+        const float eps = cfg.ln_eps;
+        c.add("ln_residual:" + pre + "mlp", 0.0, (double)M * F * 10.0, [=](cudaStream_t s) {
+          const unsigned grid = (unsigned)((M + 7) / 8);
+          SwinWin w0{};
+          DISPATCH_T(is_bf16, (swin_ln_residual_kernel<T, 0, true><<<grid, 256, 0, s>>>((const T*)yin, gp, bp, xo, M, F, eps, w0)));
+          return cudaGetLastError();
+        });
+      }
+    }
+    c.ar.reset(mk_stage);
+    c.scope = "tap" + std::to_string(st);
+    add_cast_to_half(c, x, taps[st], M * F, "cast_tap");
+    sgh /= 2;
+    sgw /= 2;
+  }
+  c.ar.reset(mk);
+  return c.ok;
+}
+
+// ReassembleModel.forward - v31_swinv2/reassembly_model.py:61-94,113-122: reshape + 3x3 projection only
+bool build_reassemble_swin(Ctx& c, const void* const taps[4], void* const maps[4], void* const maps_relu[4], int B,
+                           int gh, int gw) {
+  const dpt_config& cfg = c.m->cfg;
+  const int hd = half_dt(c);
+  for (int k = 0; k < 4 && c.ok; ++k) {
+    const std::string pre = "reasm" + std::to_string(k) + ".";
+    const Weight* fw = get_w(c, pre + "fuse.w", hd);
+    if (!fw) return false;
+    c.scope = pre;
+    GemmOp op;
+    op.A = taps[k]; op.B = B; op.Ht = gh >> k; op.Wt = gw >> k; op.C = cfg.features_per_token << k;
+    op.Wt_ptr = fw->ptr; op.N = cfg.fusion_channels; op.taps = 9; op.kpad = (int)fw->shape[1] / 9;
+    op.out = maps[k];
+    op.out2_relu = maps_relu ? maps_relu[k] : nullptr;
+    op.label = "fuse3x3";
+    add_gemm(c, op);
+  }
   return c.ok;
 }
 
@@ -707,15 +978,16 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
 // FusionModel.forward - v2_depthanything/fusion_model.py:55-80,148-154,159-220
 // The 1x1 output projection is applied before the x2 bilinear upsample (they commute: both are linear and the
 // interpolation weights sum to one), a 4x FLOP saving - SURVEY.md §8a-bis.
-bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu_in[4], void* fused, int B, int gh,
-                  int gw) {
+bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu_in[4], void* fused, int B, int h0,
+                  int w0) {
+  // h0 x w0 = size of the finest reassembly map (4x the patch grid for ViT/BEiT, the patch grid for SwinV2)
   const dpt_config& cfg = c.m->cfg;
   const int C = cfg.fusion_channels;
-  if (gh % 2 || gw % 2) return c.fail("patch grid must be even");
+  if (h0 % 8 || w0 % 8) return c.fail("reassembly map size must be divisible by 8");
   const int hd = half_dt(c);
   const size_t mk = c.ar.mark();
-  const int hs[4] = {gh * 4, gh * 2, gh, gh / 2};
-  const int ws[4] = {gw * 4, gw * 2, gw, gw / 2};
+  const int hs[4] = {h0, h0 / 2, h0 / 4, h0 / 8};
+  const int ws[4] = {w0, w0 / 2, w0 / 4, w0 / 8};
   const void* f_prev = nullptr;  // previous fusion output, already at this level's resolution
   void* f_bufs[2] = {nullptr, nullptr};
   // upsampled outputs ping-pong between two buffers sized for the largest consumer (level 0 input = 4g) ; the final
@@ -782,13 +1054,14 @@ bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu
 }
 
 // MonocularDepthHead.forward - v2_depthanything/head_model.py:61-106
-bool build_head(Ctx& c, const void* fused, void* depth, int B, int gh, int gw) {
+bool build_head(Ctx& c, const void* fused, void* depth, int B, int h, int w) {
+  // h x w = fused map size. Upsample factor: P / 8 for Depth-Anything (head_model.py:67), 2 for the MiDaS heads
+  // (v31_beit/head_model.py:43, v31_swinv2/head_model.py:43); F.interpolate output size = floor(in * scale)
   const dpt_config& cfg = c.m->cfg;
   const int C = cfg.fusion_channels, P = cfg.patch_size_px;
   const int hd = half_dt(c);
-  const int h = gh * 8, w = gw * 8;
-  // F.interpolate(scale_factor = P / 8): output size floor(in * scale)
-  const int OH = (int)floor((double)h * ((double)P / 8.0)), OW = (int)floor((double)w * ((double)P / 8.0));
+  const double scale = cfg.variant == DPT_VARIANT_DINOV2 ? (double)P / 8.0 : 2.0;
+  const int OH = (int)floor((double)h * scale), OW = (int)floor((double)w * scale);
   const Weight *w1 = get_w(c, "head.c1.w", hd), *b1 = get_w(c, "head.c1.b", DPT_F32);
   const Weight *w2 = get_w(c, "head.c2.w", hd), *b2 = get_w(c, "head.c2.b", DPT_F32);
   const Weight *w3 = get_w(c, "head.c3.w_host", DPT_F32), *b3 = get_w(c, "head.c3.b_host", DPT_F32);
@@ -829,28 +1102,46 @@ struct FwdBuffers {
   void* fused;
 };
 
+// finest reassembly-map size for a patch grid: 4x the grid (ViT / BEiT, reassembly_model.py:61-94), the grid itself
+// for SwinV2 (v31_swinv2/reassembly_model.py:61-94)
+inline int map0_scale_num(const dpt_config& cfg) { return cfg.variant == DPT_VARIANT_SWINV2 ? 1 : 4; }
+
+bool stage_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int gh, int gw) {
+  return c.m->cfg.variant == DPT_VARIANT_SWINV2 ? build_encoder_swin(c, tokens, taps, B, gh, gw)
+                                                 : build_encoder(c, tokens, taps, B, gh, gw);
+}
+bool stage_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], void* const maps_relu[4], int B, int gh,
+                      int gw) {
+  return c.m->cfg.variant == DPT_VARIANT_SWINV2 ? build_reassemble_swin(c, taps, maps, maps_relu, B, gh, gw)
+                                                 : build_reassemble(c, taps, maps, maps_relu, B, gh, gw);
+}
+
 bool build_forward(Ctx& c, const void* img, void* depth, int B, int H, int W) {
   const dpt_config& cfg = c.m->cfg;
   const int P = cfg.patch_size_px, F = cfg.features_per_token, C = cfg.fusion_channels;
+  const bool swin = cfg.variant == DPT_VARIANT_SWINV2;
   if (H % P || W % P) return c.fail("image height/width must be multiples of the patch size");
   const int gh = H / P, gw = W / P;
-  if (gh % 2 || gw % 2)
+  if (!swin && (gh % 2 || gw % 2))
     return c.fail("patch grid must be even in both directions (the reference raises inside fusion for odd grids)");
-  const int N = gh * gw + 1;
+  if (swin && (gh % 8 || gw % 8)) return c.fail("SwinV2 needs image sizes that are multiples of 32 px");
   FwdBuffers fb;
   fb.tokens = c.ar.alloc((size_t)B * gh * gw * F * 2);
-  for (int k = 0; k < 4; ++k) fb.taps[k] = c.ar.alloc((size_t)B * N * F * 2);
-  const int hs[4] = {gh * 4, gh * 2, gh, gh / 2}, ws[4] = {gw * 4, gw * 2, gw, gw / 2};
   for (int k = 0; k < 4; ++k) {
-    fb.maps[k] = c.ar.alloc((size_t)B * hs[k] * ws[k] * C * 2);
-    fb.maps_relu[k] = c.ar.alloc((size_t)B * hs[k] * ws[k] * C * 2);
+    const size_t n = swin ? (size_t)B * (gh >> k) * (gw >> k) * ((size_t)F << k) : (size_t)B * (gh * gw + 1) * F;
+    fb.taps[k] = c.ar.alloc(n * 2);
   }
-  fb.fused = c.ar.alloc((size_t)B * gh * 8 * gw * 8 * C * 2);
+  const int h0 = gh * map0_scale_num(cfg), w0 = gw * map0_scale_num(cfg);
+  for (int k = 0; k < 4; ++k) {
+    fb.maps[k] = c.ar.alloc((size_t)B * (h0 >> k) * (w0 >> k) * C * 2);
+    fb.maps_relu[k] = c.ar.alloc((size_t)B * (h0 >> k) * (w0 >> k) * C * 2);
+  }
+  fb.fused = c.ar.alloc((size_t)B * h0 * 2 * w0 * 2 * C * 2);
   if (!build_patch_embed(c, img, fb.tokens, B, H, W)) return false;
-  if (!build_encoder(c, fb.tokens, fb.taps, B, gh, gw)) return false;
-  if (!build_reassemble(c, fb.taps, fb.maps, fb.maps_relu, B, gh, gw)) return false;
-  if (!build_fusion(c, fb.maps, fb.maps_relu, fb.fused, B, gh, gw)) return false;
-  if (!build_head(c, fb.fused, depth, B, gh, gw)) return false;
+  if (!stage_encoder(c, fb.tokens, fb.taps, B, gh, gw)) return false;
+  if (!stage_reassemble(c, fb.taps, fb.maps, fb.maps_relu, B, gh, gw)) return false;
+  if (!build_fusion(c, fb.maps, fb.maps_relu, fb.fused, B, h0, w0)) return false;
+  if (!build_head(c, fb.fused, depth, B, 2 * h0, 2 * w0)) return false;
   return c.ok;
 }
 
@@ -928,7 +1219,7 @@ const char* dpt_version(void) { return "dpt_b200 0.1 (sm_100a)"; }
 
 int dpt_create(const dpt_config* cfg, dpt_handle* out) {
   if (!cfg || !out) { g_err = "null argument"; return DPT_ERR_INVALID; }
-  if (cfg->variant != DPT_VARIANT_DINOV2 && cfg->variant != DPT_VARIANT_BEIT) {
+  if (cfg->variant != DPT_VARIANT_DINOV2 && cfg->variant != DPT_VARIANT_BEIT && cfg->variant != DPT_VARIANT_SWINV2) {
     g_err = "variant not supported by this build";
     return DPT_ERR_UNSUPPORTED;
   }
@@ -1061,21 +1352,27 @@ int dpt_patch_embed(dpt_handle h, const void* img, void* tokens, void* ws, size_
 }
 int dpt_encoder(dpt_handle h, const void* tokens, void* const taps[4], void* ws, size_t ws_bytes, int B, int gh, int gw,
                 void* stream) {
-  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) { return build_encoder(c, tokens, taps, B, gh, gw); });
+  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) { return stage_encoder(c, tokens, taps, B, gh, gw); });
 }
 int dpt_reassemble(dpt_handle h, const void* const taps[4], void* const maps[4], void* ws, size_t ws_bytes, int B,
                    int gh, int gw, void* stream) {
   return build_and_run(h, ws, ws_bytes, stream,
-                       [&](Ctx& c) { return build_reassemble(c, taps, maps, nullptr, B, gh, gw); });
+                       [&](Ctx& c) { return stage_reassemble(c, taps, maps, nullptr, B, gh, gw); });
 }
 int dpt_fusion(dpt_handle h, const void* const maps[4], void* fused, void* ws, size_t ws_bytes, int B, int gh, int gw,
                void* stream) {
   return build_and_run(h, ws, ws_bytes, stream,
-                       [&](Ctx& c) { return build_fusion(c, maps, nullptr, fused, B, gh, gw); });
+                       [&](Ctx& c) {
+                         const int k = map0_scale_num(c.m->cfg);
+                         return build_fusion(c, maps, nullptr, fused, B, gh * k, gw * k);
+                       });
 }
 int dpt_head(dpt_handle h, const void* fused, void* depth, void* ws, size_t ws_bytes, int B, int gh, int gw,
              void* stream) {
-  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) { return build_head(c, fused, depth, B, gh, gw); });
+  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) {
+    const int k = 2 * map0_scale_num(c.m->cfg);
+    return build_head(c, fused, depth, B, gh * k, gw * k);
+  });
 }
 
 // ------------------------------------------------------- single operators ---------------------------------------
@@ -1106,12 +1403,12 @@ int dpt_op_conv_gemm(const void* A, const void* Wt, const float* bias, void* out
   return run_op(c, launches, stream);
 }
 
-int dpt_op_attention(const void* qkv, const void* bias, int64_t bias_ld, void* out, int B, int N, int heads,
-                     float scale, int dtype, void* stream) {
+int dpt_op_attention(const void* qkv, const void* bias, int64_t bias_ld, int bias_wmod, void* out, int B, int N,
+                     int heads, int head_dim, float scale, int dtype, void* stream) {
   std::vector<LaunchFn> launches;
   Ctx c = make_ctx(nullptr, nullptr, 0, &launches, false);
   c.is_bf16 = dtype == DPT_BF16;
-  add_attention(c, qkv, bias, bias_ld, out, B, N, heads, scale);
+  add_attention(c, qkv, bias, bias_ld, bias_wmod, out, B, N, heads, head_dim, scale);
   return run_op(c, launches, stream);
 }
 

@@ -244,6 +244,16 @@ __global__ void cast_f32_kernel(const float* __restrict__ in, T* __restrict__ ou
   }
 }
 
+// 16-bit -> fp32 (SwinV2: the residual stream starts from the normalised patch tokens), 4 elements per thread
+template <typename T>
+__global__ void cast_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, long long n4) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n4;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const T* p = in + idx * 4;
+    reinterpret_cast<float4*>(out)[idx] = make_float4(to_f32(p[0]), to_f32(p[1]), to_f32(p[2]), to_f32(p[3]));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // BEiT relative position bias (v31_beit/components/relative_positional_encoder.py:117-309):
 // out[h, i, j] = lut'[index(i, j), h], lut' = bilinear resize (align_corners=False) of the reference table

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .weights import pack_beit, pack_depthanything_v2
+from .weights import pack_beit, pack_depthanything_v2, pack_swinv2
 
 _TORCH_TO_DPT = {torch.float16: N.DPT_F16, torch.bfloat16: N.DPT_BF16}
 
@@ -37,6 +37,7 @@ class _PatchEmbedStage(_Stage):
     NORMALISATION = {
         "depthanythingv2": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
         "beit": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+        "swinv2": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),  # v31_swinv2/patch_embed.py:39-40
     }
 
     @property
@@ -52,7 +53,7 @@ class _PatchEmbedStage(_Stage):
         m = self._model
         patch = m.config["patch_size_px"]
         default_size = m.config["base_patch_grid_hw"][0] * patch
-        tiling = round(2 * patch)
+        tiling = round((8 if m.model_type == "swinv2" else 2) * patch)  # v31_swinv2/patch_embed.py:68
         if max_side_length is None:
             max_side_length = default_size
         img_h, img_w = image_bgr.shape[0:2]
@@ -92,10 +93,16 @@ class DPTModel(torch.nn.Module):
         self.model_type = model_type
         if self.config.get("is_giant", False):
             raise NotImplementedError("ViT-G (SwiGLU) is not built in this round")
-        if self.config["features_per_token"] != 64 * self.config["num_heads"]:
+        if model_type == "swinv2":
+            fs, hs = self.config["features_per_stage"], self.config["heads_per_stage"]
+            if any(f != 32 * h for f, h in zip(fs, hs)) or any(b != a * 2 for a, b in zip(fs, fs[1:])):
+                raise NotImplementedError("SwinV2 stages must have 32 features per head and double in width")
+            self.config.setdefault("features_per_token", fs[0])
+            self._packed_cpu = pack_swinv2(state_dict, self.config, strict=strict_load)
+        elif self.config["features_per_token"] != 64 * self.config["num_heads"]:
             raise NotImplementedError("the attention kernel is built for 64 features per head")
         # fp32 CPU copies in kernel layouts; moved/cast by .to()
-        if model_type == "beit":
+        elif model_type == "beit":
             self._packed_cpu = pack_beit(state_dict, self.config, strict=strict_load)
         else:
             self._packed_cpu = pack_depthanything_v2(state_dict, self.config, strict=strict_load)
@@ -168,18 +175,27 @@ class DPTModel(torch.nn.Module):
         self._release()
         with torch.cuda.device(self._device):
             cfg = N.DptConfig()
-            cfg.variant = N.VARIANT_BEIT if self.model_type == "beit" else N.VARIANT_DINOV2
+            cfg.variant = {"beit": N.VARIANT_BEIT, "swinv2": N.VARIANT_SWINV2}.get(self.model_type, N.VARIANT_DINOV2)
             cfg.dtype = _TORCH_TO_DPT[self._dtype]
             cfg.features_per_token = self.config["features_per_token"]
-            cfg.num_heads = self.config["num_heads"]
-            cfg.num_blocks = self.config["num_blocks"]
-            for i, r in enumerate(self.config["reassembly_features_list"]):
-                cfg.reassembly_features[i] = r
             cfg.fusion_channels = self.config["fusion_channels"]
             cfg.patch_size_px = self.config["patch_size_px"]
             cfg.base_grid_h, cfg.base_grid_w = self.config["base_patch_grid_hw"]
             cfg.is_metric = int(bool(self.config.get("is_metric", False)))
-            cfg.ln_eps = 1e-6
+            if self.model_type == "swinv2":
+                cfg.ln_eps = 1e-5  # torch default, all SwinV2 LayerNorms
+                cfg.window_h, cfg.window_w = self.config["window_size_hw"]
+                for i in range(4):
+                    cfg.heads_per_stage[i] = self.config["heads_per_stage"][i]
+                    cfg.layers_per_stage[i] = self.config["layers_per_stage"][i]
+                    cfg.pretrained_window[i] = self.config["pretrained_window_sizes_per_stage"][i] or 0
+                    cfg.reassembly_features[i] = self.config["features_per_stage"][i]
+            else:
+                cfg.ln_eps = 1e-6
+                cfg.num_heads = self.config["num_heads"]
+                cfg.num_blocks = self.config["num_blocks"]
+                for i, r in enumerate(self.config["reassembly_features_list"]):
+                    cfg.reassembly_features[i] = r
             handle = C.c_void_p()
             N.check(L.dpt_create(C.byref(cfg), C.byref(handle)), None, "dpt_create")
             self._handle = handle
@@ -235,10 +251,11 @@ class DPTModel(torch.nn.Module):
             raise RuntimeError(f"Data type mismatch! Image: {x.dtype}, model: {dtype}")
         p = self.config["patch_size_px"]
         B, _, H, W = x.shape
-        if H % p or W % p or (H // p) % 2 or (W // p) % 2:
+        mult = (8 if self.model_type == "swinv2" else 2) * p
+        if H % mult or W % mult:
             raise ValueError(
-                f"image size {H}x{W} is not usable: height and width must be multiples of {2 * p} "
-                "(even patch grid; the reference fails inside fusion otherwise)"
+                f"image size {H}x{W} is not usable: height and width must be multiples of {mult} "
+                "(the reference fails inside fusion otherwise)"
             )
         return B, H, W
 
@@ -357,7 +374,10 @@ class DPTModel(torch.nn.Module):
         B, Np, F = patch_tokens.shape
         assert Np == gh * gw and patch_tokens.dtype == self._dtype
         tok = patch_tokens.contiguous()
-        taps = [torch.empty((B, Np + 1, F), dtype=self._dtype, device=self._device) for _ in range(4)]
+        if self.model_type == "swinv2":  # hierarchical taps, no cls token (v31_swinv2/image_encoder_model.py:77-98)
+            taps = [torch.empty((B, (gh >> k) * (gw >> k), F << k), dtype=self._dtype, device=self._device) for k in range(4)]
+        else:
+            taps = [torch.empty((B, Np + 1, F), dtype=self._dtype, device=self._device) for _ in range(4)]
         ws = self._stage_ws(B, gh, gw)
         rc = N.lib().dpt_encoder(self._handle, C.c_void_p(tok.data_ptr()), C.byref(N.ptr4(taps)),
                                  C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
@@ -377,7 +397,8 @@ class DPTModel(torch.nn.Module):
         B = s1.shape[0]
         Cc = self.config["fusion_channels"]
         taps = [t.contiguous() for t in (s1, s2, s3, s4)]
-        sizes = [(gh * 4, gw * 4), (gh * 2, gw * 2), (gh, gw), (gh // 2, gw // 2)]
+        k0 = 1 if self.model_type == "swinv2" else 4
+        sizes = [((gh * k0) >> k, (gw * k0) >> k) for k in range(4)]
         maps = [self._nhwc_empty(B, Cc, h, w) for h, w in sizes]
         ws = self._stage_ws(B, gh, gw)
         rc = N.lib().dpt_reassemble(self._handle, C.byref(N.ptr4(taps)), C.byref(N.ptr4(maps)),
@@ -387,9 +408,10 @@ class DPTModel(torch.nn.Module):
 
     def _stage_fusion(self, r1, r2, r3, r4):
         maps = [self._as_nhwc(t) for t in (r1, r2, r3, r4)]
-        B, Cc, h3, w3 = maps[2].shape
-        gh, gw = h3, w3
-        fused = self._nhwc_empty(B, Cc, gh * 8, gw * 8)
+        B, Cc, h0, w0 = maps[0].shape
+        k0 = 1 if self.model_type == "swinv2" else 4
+        gh, gw = h0 // k0, w0 // k0
+        fused = self._nhwc_empty(B, Cc, h0 * 2, w0 * 2)
         ws = self._stage_ws(B, gh, gw)
         rc = N.lib().dpt_fusion(self._handle, C.byref(N.ptr4(maps)), C.c_void_p(fused.data_ptr()),
                                 C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
@@ -399,7 +421,8 @@ class DPTModel(torch.nn.Module):
     def _stage_head(self, fused: torch.Tensor):
         x = self._as_nhwc(fused)
         B, Cc, h, w = x.shape
-        gh, gw = h // 8, w // 8
+        k0 = 2 if self.model_type == "swinv2" else 8
+        gh, gw = h // k0, w // k0
         p = self.config["patch_size_px"]
         depth = torch.empty((B, gh * p, gw * p), dtype=self._dtype, device=self._device)
         ws = self._stage_ws(B, gh, gw)

@@ -15,6 +15,7 @@ from .dpt_model import DPTModel
 from .weights import (
     determine_model_type_from_state_dict,
     get_model_config_from_midas_beit_state_dict,
+    get_model_config_from_midas_swinv2_state_dict,
     get_model_config_from_state_dict,
 )
 
@@ -38,9 +39,11 @@ def make_dpt_from_state_dict(
         raise NotImplementedError(f"Bad model type: {model_type}, no support for this yet!")
     if model_type == "beit":
         return make_beit_dpt_from_midas_v31_state_dict(state_dict, enable_cache, enable_optimizations, strict_load)
+    if model_type == "swinv2":
+        return make_swinv2_dpt_from_midas_v31_state_dict(state_dict, enable_cache, enable_optimizations, strict_load)
     if model_type != "depthanythingv2":
         raise NotImplementedError(
-            f"Model type {model_type} is recognised but its B200 encoder is not built yet (SURVEY.md section 8: configs W/E, 8f)"
+            f"Model type {model_type} is recognised but its B200 encoder is not built yet (SURVEY.md section 8f)"
         )
 
     # metric models are indistinguishable by weights; the reference keys off the file name (make_dpt.py:56-66)
@@ -82,4 +85,19 @@ def make_beit_dpt_from_midas_v31_state_dict(
               "  Some weights may be missing or unused!", sep="\n", flush=True)
     config_dict = get_model_config_from_midas_beit_state_dict(midas_v31_state_dict, enable_cache, enable_optimizations)
     model = DPTModel(config_dict, midas_v31_state_dict, strict_load=strict_load, model_type="beit")
+    return config_dict, model
+
+
+def make_swinv2_dpt_from_midas_v31_state_dict(
+    midas_v31_state_dict: dict,
+    enable_cache: bool = False,
+    enable_optimizations: bool = True,
+    strict_load: bool = True,
+) -> tuple[dict, DPTModel]:
+    """make_swinv2_dpt.py:24-58. Bias tables / shift masks are rebuilt on the device for every layer and grid size."""
+    if not strict_load:
+        print("", "WARNING:", "  Loading model weights without 'strict' mode enabled!",
+              "  Some weights may be missing or unused!", sep="\n", flush=True)
+    config_dict = get_model_config_from_midas_swinv2_state_dict(midas_v31_state_dict, enable_cache, enable_optimizations)
+    model = DPTModel(config_dict, midas_v31_state_dict, strict_load=strict_load, model_type="swinv2")
     return config_dict, model

@@ -348,3 +348,130 @@ def pack_beit(sd: dict, cfg: dict, strict: bool = True) -> dict:
                                (" ..." if len(missing) > 8 else ""))
         raise RuntimeError("non-strict loading of BEiT checkpoints with missing keys is not supported: " + missing[0])
     return out
+
+
+# =====================================================================================================================
+# MiDaS v3.1 SwinV2 (muggled_dpt/v31_swinv2/state_dict_conversion/*): config inference + packing
+# =====================================================================================================================
+
+
+def get_model_config_from_midas_swinv2_state_dict(state_dict: dict, enable_cache: bool, enable_optimizations: bool) -> dict:
+    """config_from_midas_state_dict.py:17-214 - same keys, same order as the reference's SwinV2 config dict. Window
+    size and base grid come from the first stored `attn_mask` ([nW, A, A]); the pretrained-window LUT is the reference's."""
+    pe_key = "pretrained.model.patch_embed.proj.weight"
+    assert pe_key in state_dict, f"Error determining transformer features per token! Couldn't find {pe_key} key"
+    f0, patch = int(state_dict[pe_key].shape[0]), int(state_dict[pe_key].shape[3])
+    heads, layers = {}, {}
+    for k in state_dict:
+        m = re.match(r"pretrained\.model\.layers\.(\d+)\.blocks\.(\d+)\.", k)
+        if m:
+            st, bi = int(m.group(1)), int(m.group(2))
+            layers[st] = max(layers.get(st, 0), bi + 1)
+            if k.endswith("logit_scale"):
+                heads[st] = int(state_dict[k].shape[0])
+    assert len(heads) == 4, f"Expecting 4 stages in swinv2 dpt, got: {len(heads)}"
+    assert len(layers) == 4, f"Expecting 4 stages in swinv2 dpt, got: {len(layers)}"
+    mask_keys = sorted(k for k in state_dict if k.endswith("attn_mask"))
+    assert mask_keys, "Error, couldn't find attn_mask key, can't determine window size!"
+    num_windows, window_area = state_dict[mask_keys[0]].shape[0:2]
+    win = int(math.sqrt(int(window_area)))
+    base = int(math.sqrt(int(num_windows) * int(window_area)))
+    pretrained = {16: [16, 16, 16, 8], 24: [12, 12, 12, 6]}.get(win, [None] * 4)
+    lrn = "scratch.layer1_rn.weight"
+    assert lrn in state_dict, f"Error determining fusion channel count! Couldn't find {lrn} key"
+    return {
+        "features_per_stage": [f0 * (2**i) for i in range(4)],
+        "heads_per_stage": [heads[i] for i in range(4)],
+        "layers_per_stage": [layers[i] for i in range(4)],
+        "base_patch_grid_hw": (base, base),
+        "window_size_hw": (win, win),
+        "pretrained_window_sizes_per_stage": pretrained,
+        "fusion_channels": int(state_dict[lrn].shape[0]),
+        "patch_size_px": patch,
+        "enable_cache": enable_cache,
+        "enable_optimizations": enable_optimizations,
+    }
+
+
+def pack_swinv2(sd: dict, cfg: dict, strict: bool = True) -> dict:
+    """Returns {packed name: (fp32 cpu tensor, kind)}. Mirrors convert_midas_state_dict_keys.py: stored `attn_mask`
+    tensors are dropped (:179-181), `logit_scale` is clamped at ln(100) and exponentiated once (:115-131), q/v biases
+    become the bias of the fused QKV GEMM."""
+    missing = []
+
+    def get(key):
+        if key in sd:
+            return sd[key].detach().to(torch.float32).cpu()
+        missing.append(key)
+        return None
+
+    out = {}
+
+    def put(name, t, kind):
+        if t is not None:
+            out[name] = (t.contiguous(), kind)
+
+    def lin(key):
+        w = get(key)
+        return pack_linear(w.reshape(w.shape[0], -1)) if w is not None else None
+
+    def conv(key):
+        w = get(key)
+        return pack_conv(w) if w is not None else None
+
+    pw = get("pretrained.model.patch_embed.proj.weight")
+    put("patch.w", pack_patch_embed(pw) if pw is not None else None, "half")
+    put("patch.b", get("pretrained.model.patch_embed.proj.bias"), "f32")
+    put("patch.ln.w", get("pretrained.model.patch_embed.norm.weight"), "f32")
+    put("patch.ln.b", get("pretrained.model.patch_embed.norm.bias"), "f32")
+    for st in range(4):
+        Fs = cfg["features_per_stage"][st]
+        for bi in range(cfg["layers_per_stage"][st]):
+            s, d = f"pretrained.model.layers.{st}.blocks.{bi}.", f"sw{st}.{bi}."
+            put(d + "qkv.w", lin(s + "attn.qkv.weight"), "half")
+            qb, vb = get(s + "attn.q_bias"), get(s + "attn.v_bias")
+            if qb is not None and vb is not None:
+                put(d + "qkv.b", torch.cat([qb.reshape(-1), torch.zeros(Fs), vb.reshape(-1)]), "f32")
+            ls = get(s + "attn.logit_scale")
+            if ls is not None:
+                put(d + "logit", torch.clamp(ls.reshape(-1), max=math.log(1.0 / 0.01)).exp(), "f32")
+            put(d + "cpb.w1", get(s + "attn.cpb_mlp.0.weight"), "f32")
+            put(d + "cpb.b1", get(s + "attn.cpb_mlp.0.bias"), "f32")
+            put(d + "cpb.w2", get(s + "attn.cpb_mlp.2.weight"), "f32")
+            put(d + "proj.w", lin(s + "attn.proj.weight"), "half")
+            put(d + "proj.b", get(s + "attn.proj.bias"), "f32")
+            put(d + "ln1.w", get(s + "norm1.weight"), "f32")
+            put(d + "ln1.b", get(s + "norm1.bias"), "f32")
+            put(d + "ln2.w", get(s + "norm2.weight"), "f32")
+            put(d + "ln2.b", get(s + "norm2.bias"), "f32")
+            put(d + "fc1.w", lin(s + "mlp.fc1.weight"), "half")
+            put(d + "fc1.b", get(s + "mlp.fc1.bias"), "f32")
+            put(d + "fc2.w", lin(s + "mlp.fc2.weight"), "half")
+            put(d + "fc2.b", get(s + "mlp.fc2.bias"), "f32")
+        if st < 3:
+            s, d = f"pretrained.model.layers.{st}.downsample.", f"sw{st}.merge."
+            put(d + "w", lin(s + "reduction.weight"), "half")
+            put(d + "ln.w", get(s + "norm.weight"), "f32")
+            put(d + "ln.b", get(s + "norm.bias"), "f32")
+    for k in range(4):
+        put(f"reasm{k}.fuse.w", conv(f"scratch.layer{k + 1}_rn.weight"), "half")
+    for lvl in range(4):
+        s, d = f"scratch.refinenet{lvl + 1}.", f"fus{lvl}."
+        units = (("rcu1", "resConfUnit1"), ("rcu2", "resConfUnit2")) if lvl < 3 else (("rcu2", "resConfUnit2"),)
+        for dn, sn in units:
+            for cv in (1, 2):
+                put(f"{d}{dn}.c{cv}.w", conv(f"{s}{sn}.conv{cv}.weight"), "half")
+                put(f"{d}{dn}.c{cv}.b", get(f"{s}{sn}.conv{cv}.bias"), "f32")
+        put(d + "out.w", lin(s + "out_conv.weight"), "half")
+        put(d + "out.b", get(s + "out_conv.bias"), "f32")
+    put("head.c1.w", conv("scratch.output_conv.0.weight"), "half")
+    put("head.c1.b", get("scratch.output_conv.0.bias"), "f32")
+    put("head.c2.w", conv("scratch.output_conv.2.weight"), "half")
+    put("head.c2.b", get("scratch.output_conv.2.bias"), "f32")
+    w = get("scratch.output_conv.4.weight")
+    put("head.c3.w_host", w.reshape(-1) if w is not None else None, "host")
+    put("head.c3.b_host", get("scratch.output_conv.4.bias"), "host")
+    if missing:
+        raise RuntimeError("Error(s) in loading state_dict: Missing key(s): " + ", ".join(missing[:8]) +
+                           (" ..." if len(missing) > 8 else ""))
+    return out

@@ -29,16 +29,18 @@ def conv_gemm(A, Wt, bias=None, add1=None, add2=None, want_relu=False, taps=1, x
     return (out, out_relu) if want_relu else out
 
 
-def attention(qkv, heads, scale, bias=None):
+def attention(qkv, heads, scale, bias=None, head_dim=64, bias_wmod=1):
+    """bias: [heads, n, n] or [bias_wmod, heads, n, n]"""
     B, n, F3 = qkv.shape
     out = torch.empty((B, n, F3 // 3), device=qkv.device, dtype=qkv.dtype)
     ld = 0
     if bias is not None:  # pad rows to a multiple of 128 columns (kernel contract)
         ld = (n + 127) // 128 * 128
-        padded = torch.zeros((bias.shape[0], n, ld), device=bias.device, dtype=bias.dtype)
-        padded[:, :, :n] = bias
+        padded = torch.zeros(tuple(bias.shape[:-1]) + (ld,), device=bias.device, dtype=bias.dtype)
+        padded[..., :n] = bias
         bias = padded
-    rc = N.lib().dpt_op_attention(_p(qkv), _p(bias), ld, _p(out), B, n, heads, float(scale), DT[qkv.dtype], _stream())
+    rc = N.lib().dpt_op_attention(_p(qkv), _p(bias), ld, bias_wmod, _p(out), B, n, heads, head_dim, float(scale),
+                                  DT[qkv.dtype], _stream())
     N.check(rc, None, "dpt_op_attention")
     torch.cuda.synchronize()
     return out

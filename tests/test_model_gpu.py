@@ -227,3 +227,89 @@ def test_beit_base_384_against_oracle():
     print(f"beit_base_384 bf16: rel_l2={e[0]:.3e} max_abs={e[1]:.3e} max_rel={e[2]:.3e}")
     assert tuple(depth.shape) == (2, 384, 384)
     assert e[0] < 2 * REL_L2[torch.bfloat16], e
+
+
+# ------------------------------------------------------------------------------------------------ MiDaS v3.1 SwinV2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("name", ["swinv2_micro_a.pt", "swinv2_micro_b.pt"])
+def test_swinv2_micro_stagewise_against_reference_golden(name, dtype):
+    from oracle import dpt_oracle as O
+
+    fix = torch.load(os.path.join(GOLDEN, name))
+    sd = O.make_synthetic_state_dict_swinv2(fix["sd_name"], fix["sd_seed"])
+    cfg, model = _load_model(sd, dtype, name="dpt_swin2_synth.pt")
+    assert model.model_type == "swinv2"
+    img = fix["img"].to("cuda", dtype)
+    report = {}
+    with torch.inference_mode():
+        tokens, grid_hw = model.patch_embed(img)
+        assert tuple(grid_hw) == tuple(fix["grid_hw"])
+        report["tokens"] = _err(tokens, fix["tokens"])
+        taps = model.imgencoder(fix["tokens"].to("cuda", dtype), grid_hw)
+        for i in range(4):
+            assert tuple(taps[i].shape) == tuple(fix["taps"][i].shape)
+            report[f"tap{i}"] = _err(taps[i], fix["taps"][i])
+        maps = model.reassemble(*[t.to("cuda", dtype) for t in fix["taps"]], grid_hw)
+        for i in range(4):
+            assert tuple(maps[i].shape) == tuple(fix["maps"][i].shape)
+            report[f"map{i}"] = _err(maps[i], fix["maps"][i])
+        fused = model.fusion(*[t.to("cuda", dtype) for t in fix["maps"]])
+        report["fused"] = _err(fused, fix["fused"])
+        depth = model.head(fix["fused"].to("cuda", dtype))
+        report["head"] = _err(depth, fix["depth"])
+        full = model(img)
+        assert tuple(full.shape) == tuple(fix["depth"].shape)
+        report["depth_e2e"] = _err(full, fix["depth"])
+    for k, v in report.items():
+        print(f"{name} {dtype} {k}: rel_l2={v[0]:.3e} max_abs={v[1]:.3e} max_rel={v[2]:.3e}")
+    # The fixture's logit scales reach the ln(100) clamp: logits of +-100 make the softmax so peaked that the 16-bit
+    # rounding of the normalised q/k dominates. The reference's OWN 16-bit CPU forward on these weights is off by
+    # 2.2e-2 .. 1.1e-1 (bf16) / 0.9e-2 .. 5e-2 (fp16) on the four taps and 7.2e-2 / 2.5e-2 on the depth map
+    # (measured with the reference in the build container); the encoder gates are set below those figures.
+    enc_tol = {torch.bfloat16: 0.12, torch.float16: 0.02}[dtype]
+    e2e_tol = {torch.bfloat16: 0.08, torch.float16: 0.02}[dtype]
+    for k, v in report.items():
+        tol = enc_tol if k.startswith("tap") else (e2e_tol if k == "depth_e2e" else REL_L2[dtype])
+        assert v[0] < tol, (k, v)
+
+
+def test_swinv2_micro_mild_logit_scale_tight_tolerance():
+    """same architecture with logit scales around 10 (no clamp): the usual per-stage tolerances apply, which is what
+    would catch a wrong window / shift / mask / bias index"""
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict_swinv2("swinv2_micro", seed=21, logit_std=0.3)
+    for shape in ((2, 128, 128), (1, 128, 160)):
+        img = O.make_input(*shape, seed=5)
+        st = O.forward_swinv2(sd, img, return_stages=True)
+        cfg, model = _load_model(sd, torch.float16, name="dpt_swin2_mild.pt")
+        with torch.inference_mode():
+            tokens, grid_hw = model.patch_embed(img.to("cuda", torch.float16))
+            taps = model.imgencoder(st["tokens"].to("cuda", torch.float16), grid_hw)
+            depth = model(img.to("cuda", torch.float16))
+        for i in range(4):
+            e = _err(taps[i], st["taps"][i])
+            print(f"swinv2 mild {shape} tap{i}: rel_l2={e[0]:.3e}")
+            assert e[0] < 2 * REL_L2[torch.float16], (i, e)
+        e = _err(depth, st["depth"])
+        print(f"swinv2 mild {shape} depth: rel_l2={e[0]:.3e} max_rel={e[2]:.3e}")
+        assert e[0] < 2 * REL_L2[torch.float16], e
+
+
+def test_swinv2_tiny_256_against_oracle():
+    """config W shape family (BASELINE.json configs[3]): windowed cosine attention, here the SwinV2-T architecture
+    (window 16, heads 3/6/12/24 incl. an odd head count) at 256x256, batch 2, fp16, vs the fp32 oracle"""
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict_swinv2("swinv2_tiny_256", seed=6)
+    img = O.make_input(2, 256, 256, seed=8)
+    ref = O.forward_swinv2(sd, img)
+    cfg, model = _load_model(sd, torch.float16, name="dpt_swin2_tiny_256.pt")
+    with torch.inference_mode():
+        depth = model(img.to("cuda", torch.float16))
+    e = _err(depth, ref)
+    print(f"swinv2_tiny_256 fp16: rel_l2={e[0]:.3e} max_abs={e[1]:.3e} max_rel={e[2]:.3e}")
+    assert tuple(depth.shape) == (2, 256, 256)
+    assert e[0] < 0.03, e  # clamp-reaching logit scales, see the note in the micro test

@@ -169,3 +169,19 @@ def test_resize_bilinear_align_corners(IH, IW, OH, OW):
     ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(OH, OW), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
     rel, mx = rel_err(y, ref)
     assert rel < 4e-3, (rel, mx)
+
+
+def test_attention_head_dim_32_with_window_bias():
+    """SwinV2 shape: 32 features per head, per-window additive bias tables (b % n_windows)"""
+    from gpu_util import attention, rel_err
+
+    nW, B, N, heads = 4, 2, 144, 3
+    Fd = heads * 32
+    qkv = _mk((B * nW, N, 3 * Fd), torch.bfloat16, 31, 0.5)
+    bias = _mk((nW, heads, N, N), torch.bfloat16, 32)
+    out = attention(qkv, heads, 1.0, bias=bias, head_dim=32, bias_wmod=nW)
+    q, k, v = qkv.float().reshape(B * nW, N, 3, heads, 32).permute(2, 0, 3, 1, 4).unbind(0)
+    a = q @ k.transpose(-2, -1) + bias.float().repeat(B, 1, 1, 1)
+    ref = (a.softmax(-1) @ v).transpose(1, 2).reshape(B * nW, N, Fd)
+    rel, mx = rel_err(out, ref)
+    assert rel < 1e-2, (rel, mx)

@@ -93,3 +93,33 @@ def test_beit_relative_position_index_special_rows():
     assert (idx[0, 1:] == top + 1).all() and (idx[1:, 0] == top + 2).all() and idx[0, 0] == top + 3
     assert idx[1:, 1:].min() == 0 and idx[1:, 1:].max() == top
     assert (idx[1:, 1:].diagonal() == (3 - 1) * (2 * 4 - 1) + (4 - 1)).all()  # zero offset
+
+
+@pytest.mark.parametrize("name", ["swinv2_micro_a.pt", "swinv2_micro_b.pt"])
+def test_swinv2_oracle_matches_reference_every_stage(name):
+    from oracle.make_golden import state_dict_checksum
+
+    fix = torch.load(os.path.join(GOLDEN, name))
+    sd = O.make_synthetic_state_dict_swinv2(fix["sd_name"], fix["sd_seed"])
+    assert state_dict_checksum(sd) == fix["sd_checksum"]
+    st = O.forward_swinv2(sd, fix["img"], return_stages=True)
+    assert tuple(st["grid_hw"]) == tuple(fix["grid_hw"])
+    torch.testing.assert_close(st["tokens"], fix["tokens"], rtol=0, atol=1e-5)
+    for a, b in zip(st["taps"], fix["taps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-4)
+    for a, b in zip(st["maps"], fix["maps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=2e-4)
+    torch.testing.assert_close(st["depth"], fix["depth"], rtol=0, atol=5e-4)
+
+
+def test_swin_window_and_shift_rules():
+    # adjust_window_and_shift_sizes (windowed_attention.py:345-388): SwinV2-L @384 (grids 96/48/24/12, target 24)
+    assert O.swin_window_and_shift((96, 96), (24, 24)) == ((24, 24), (12, 12))
+    assert O.swin_window_and_shift((24, 24), (24, 24)) == ((24, 24), (0, 0))
+    assert O.swin_window_and_shift((12, 12), (24, 24)) == ((12, 12), (0, 0))
+    # non-tiling grid: closest divisor of the grid in [win/2, 2 win)
+    assert O.swin_window_and_shift((32, 20), (8, 8)) == ((8, 10), (4, 5))
+    m = O.swin_shift_mask((16, 16), (8, 8), (4, 4))
+    assert m.shape == (4, 64, 64) and set(m.unique().tolist()) == {-100.0, 0.0}
+    assert (m[0] == 0).all()  # the top-left window never wraps
+    assert O.swin_shift_mask((8, 8), (8, 8), (0, 0)) is None

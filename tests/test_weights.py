@@ -166,3 +166,33 @@ def test_beit_factory_surface_on_cpu():
         cfg, model = make_dpt_from_state_dict(path)
     assert model.model_type == "beit" and cfg["num_heads"] == 2 and cfg["base_patch_grid_hw"] == (6, 6)
     assert model.patch_embed.rgb_offset == (0.5, 0.5, 0.5)
+
+
+def test_swinv2_config_and_packing():
+    import math
+
+    sd = O.make_synthetic_state_dict_swinv2("swinv2_micro", seed=4)
+    cfg = Wt.get_model_config_from_midas_swinv2_state_dict(sd, False, True)
+    assert list(cfg.keys()) == ["features_per_stage", "heads_per_stage", "layers_per_stage", "base_patch_grid_hw",
+                                "window_size_hw", "pretrained_window_sizes_per_stage", "fusion_channels",
+                                "patch_size_px", "enable_cache", "enable_optimizations"]
+    ocfg = O.infer_config_swinv2(sd)
+    for k, v in ocfg.items():
+        assert cfg[k] == v, k
+    packed = Wt.pack_swinv2(sd, cfg)
+    assert not any("attn_mask" in k for k in packed)
+    # logit_scale: clamp at ln(100) then exp, once, at load (convert_midas_state_dict_keys.py:115-131)
+    raw = sd["pretrained.model.layers.3.blocks.1.attn.logit_scale"].reshape(-1)
+    got = packed["sw3.1.logit"][0]
+    torch.testing.assert_close(got, torch.clamp(raw, max=math.log(100.0)).exp())
+    assert got.max() <= 100.0 + 1e-4
+    assert packed["sw0.merge.w"][0].shape == (64, 128)  # Linear(4C, 2C), K padded to 64-multiples
+    # known pretrained-window LUT for the shipped checkpoints
+    big = {"pretrained.model.patch_embed.proj.weight": torch.zeros(192, 3, 4, 4), "scratch.layer1_rn.weight": torch.zeros(256, 192, 3, 3)}
+    for st, (h, n) in enumerate(zip((6, 12, 24, 48), (2, 2, 18, 2))):
+        for bi in range(n):
+            big[f"pretrained.model.layers.{st}.blocks.{bi}.attn.logit_scale"] = torch.zeros(h, 1, 1)
+    big["pretrained.model.layers.0.blocks.1.attn_mask"] = torch.zeros(16, 576, 1)
+    c2 = Wt.get_model_config_from_midas_swinv2_state_dict(big, False, True)
+    assert c2["window_size_hw"] == (24, 24) and c2["base_patch_grid_hw"] == (96, 96)
+    assert c2["pretrained_window_sizes_per_stage"] == [12, 12, 12, 6] and c2["layers_per_stage"] == [2, 2, 18, 2]
