@@ -294,24 +294,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) l2[i] = __fmul2_rn(l2[i], b2);
       }
-      // ---- P = exp2(s*c - mu) (<= 256) and the row sum, kept packed in registers while P_{j-1} V_{j-1} finishes
+      // ---- P = exp2(s*c - mu) (<= 256) in place, in three sweeps (scale/shift, ex2, sum + pack) so that the MUFU
+      //      results are consumed long after they are issued; kept packed in registers while P_{j-1} V_{j-1} finishes
       const float2 neg_mu2 = make_float2(-mu, -mu);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 x = make_float2(__uint_as_float(sv[ci][i]), __uint_as_float(sv[ci][i + 1]));
+          float2 e;
+          if constexpr (HAS_BIAS) e = __fadd2_rn(x, neg_mu2);  // bias and scale already applied
+          else e = __ffma2_rn(x, c2, neg_mu2);
+          sv[ci][i] = __float_as_uint(e.x);
+          sv[ci][i + 1] = __float_as_uint(e.y);
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[ci][i] = __float_as_uint(ex2_approx(__uint_as_float(sv[ci][i])));  // ex2(-inf) = 0
+      }
       uint32_t pk[64];
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 x = make_float2(__uint_as_float(sv[ci][8 * g + 2 * i]), __uint_as_float(sv[ci][8 * g + 2 * i + 1]));
-            float2 pf;
-            if constexpr (HAS_BIAS) pf = __fadd2_rn(x, neg_mu2);  // bias and scale already applied
-            else pf = __ffma2_rn(x, c2, neg_mu2);
-            pf.x = ex2_approx(pf.x);  // ex2(-inf) = 0 for the masked tail
-            pf.y = ex2_approx(pf.y);
-            l2[i] = __fadd2_rn(l2[i], pf);
-            pk[ci * 16 + g * 4 + i] = pack2(pf.x, pf.y, is_bf16);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float2 pf = make_float2(__uint_as_float(sv[ci][2 * i]), __uint_as_float(sv[ci][2 * i + 1]));
+          l2[i & 3] = __fadd2_rn(l2[i & 3], pf);
+          pk[ci * 16 + i] = pack2(pf.x, pf.y, is_bf16);
         }
       }
       // ---- the previous P@V must be complete: it reads the P buffer and writes the accumulator
