@@ -173,6 +173,40 @@ cudaError_t launch_gemm_inst(const GemmParams& p, int grid, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// 2-CTA (cta_group::2) variant: BLOCK_N = 256, launched as clusters of two CTAs
+template <int OUT_KIND, int ACT, bool BF16>
+cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<256, OUT_KIND, ACT, BF16, true>;
+  constexpr int smem = GemmCfg<256, true>::SMEM_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <bool BF16>
+cudaError_t launch_gemm2_dt(const GemmParams& p, int grid, cudaStream_t s) {
+  if (p.out_kind == OUT_F32) return launch_gemm2_inst<OUT_F32, ACT_NONE, BF16>(p, grid, s);
+  if (p.act == ACT_GELU) return launch_gemm2_inst<OUT_HALF, ACT_GELU, BF16>(p, grid, s);
+  if (p.act == ACT_RELU) return launch_gemm2_inst<OUT_HALF, ACT_RELU, BF16>(p, grid, s);
+  return launch_gemm2_inst<OUT_HALF, ACT_NONE, BF16>(p, grid, s);
+}
+
 template <int BN, bool BF16>
 cudaError_t launch_gemm_bn(const GemmParams& p, int grid, cudaStream_t s) {
   if (p.out_kind == OUT_F32) return launch_gemm_inst<BN, OUT_F32, ACT_NONE, BF16>(p, grid, s);
@@ -192,8 +226,18 @@ cudaError_t launch_gemm_dt(const GemmParams& p, int bn, int grid, cudaStream_t s
   }
 }
 
-cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, cudaStream_t s) {
+cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, bool two_cta, cudaStream_t s) {
+  if (two_cta) return p.is_bf16 ? launch_gemm2_dt<true>(p, grid, s) : launch_gemm2_dt<false>(p, grid, s);
   return p.is_bf16 ? launch_gemm_dt<true>(p, bn, grid, s) : launch_gemm_dt<false>(p, bn, grid, s);
+}
+
+bool two_cta_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_GEMM_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // Description of one spatial GEMM (see gemm_tc.cuh).
@@ -256,11 +300,16 @@ bool add_gemm(Ctx& c, GemmOp op) {
     uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
     if (!make_tmap(&p.tmA, op.A, 4, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
   }
+  // CTA pairs (cta_group::2, 256 x 256 tiles) when the problem is wide and tall enough to fill the machine with pairs
+  const long long m_tiles_all = (long long)op.B * ((op.W + TW - 1) / TW) * ((op.H + TH - 1) / TH);
+  const int n_tiles_all = (op.N + bn - 1) / bn;
+  const bool two_cta = two_cta_enabled() && bn == 256 && op.out_kind != OUT_HEAD &&
+                       ((m_tiles_all + 1) / 2) * n_tiles_all >= c.num_sms / 2;
   {
     const uint64_t ktot = (uint64_t)op.taps * op.kpad;
     uint64_t dims[2] = {ktot, (uint64_t)op.N};
     uint64_t str[1] = {ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, (uint32_t)(two_cta ? bn / 2 : bn)};
     if (!make_tmap(&p.tmB, op.Wt_ptr, 2, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
   }
   p.W = op.W; p.H = op.H; p.B = op.B;
@@ -288,7 +337,8 @@ bool add_gemm(Ctx& c, GemmOp op) {
   p.head_act = op.head_act;
 
   const long long total = (long long)p.B * p.tiles_y * p.tiles_x * p.n_tiles;
-  const int grid = (int)std::min<long long>(total, c.num_sms);
+  int grid = (int)std::min<long long>(total, c.num_sms);
+  if (two_cta) grid = (int)std::min<long long>(2 * ((m_tiles_all + 1) / 2) * n_tiles_all, c.num_sms & ~1);
   {
     const double pix = (double)op.B * op.H * op.W;
     const double flops = 2.0 * pix * op.N * op.C * op.taps;
@@ -298,8 +348,8 @@ bool add_gemm(Ctx& c, GemmOp op) {
     if (op.add1) bytes += pix * op.N * osz;
     if (op.add2) bytes += pix * op.N * 2.0;
     if (op.out2_relu) bytes += pix * op.N * 2.0;
-    c.add("gemm" + std::to_string(bn) + ":" + c.scope + op.label, flops, bytes,
-          [p, bn, grid](cudaStream_t s) { return launch_gemm(p, bn, grid, s); });
+    c.add(std::string(two_cta ? "gemm256x2" : "gemm" + std::to_string(bn)) + ":" + c.scope + op.label, flops, bytes,
+          [p, bn, grid, two_cta](cudaStream_t s) { return launch_gemm(p, bn, grid, two_cta, s); });
   }
   return true;
 }

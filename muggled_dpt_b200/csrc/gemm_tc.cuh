@@ -33,7 +33,7 @@ enum : int { OUT_HALF = 0, OUT_F32 = 1, OUT_HEAD = 2 };
 
 struct __align__(64) GemmParams {
   CUtensorMap tmA;  // 4-D (C, W, H, B), box (64, TW, TH, 1), 128B swizzle
-  CUtensorMap tmB;  // 2-D (taps*kpad, N), box (64, BLOCK_N), 128B swizzle
+  CUtensorMap tmB;  // 2-D (taps*kpad, N), box (64, BLOCK_N) - (64, BLOCK_N/2) for the 2-CTA kernel -, 128B swizzle
   int W, H, B;      // input spatial extent used for M tiling (and output-row validity)
   int tw_log2;      // TW = 1 << tw_log2, TH = 128 >> tw_log2
   int tiles_x, tiles_y;
@@ -61,11 +61,14 @@ struct __align__(64) GemmParams {
   int head_act;       // ACT_RELU or ACT_SIGMOID
 };
 
-template <int BLOCK_N>
+// TWO_CTA: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of
+// A and HALF of the B tile (the tensor core reads the other half from the peer's shared memory), which cuts the
+// L2 -> SM operand traffic per FLOP by a third and buys two more pipeline stages.
+template <int BLOCK_N, bool TWO_CTA = false>
 struct GemmCfg {
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int STAGES = TWO_CTA ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = (TWO_CTA ? BLOCK_N / 2 : BLOCK_N) * GEMM_BLOCK_K * 2;
   static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP;
   static constexpr int BAR_BYTES = 256 + 2 * BLOCK_N * 4;  // mbarriers + tmem ptr, bias tile [2][BLOCK_N]
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + BAR_BYTES;
@@ -125,9 +128,10 @@ DPT_DEVICE float2 unpack2(uint32_t u, int is_bf16) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int BLOCK_N, int OUT_KIND, int ACT, bool BF16>
+template <int BLOCK_N, int OUT_KIND, int ACT, bool BF16, bool TWO_CTA = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, TWO_CTA>;
+  static_assert(!TWO_CTA || BLOCK_N == 256, "the 2-CTA kernel is built for BLOCK_N = 256");
   constexpr int STAGES = Cfg::STAGES;
 
   // no static shared memory in this kernel: the dynamic segment starts at the CTA's (1024-aligned) window base;
@@ -148,8 +152,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
 
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
-  const int total_tiles = m_tiles * p.n_tiles;
   const int num_kb = p.num_taps * p.kchunks;
+  // Work items: tiles for the 1-CTA kernel; for the 2-CTA kernel a pair of vertically adjacent M-tiles
+  // (m_tile = 2 * pair + cta_rank; an odd trailing M-tile computes against zero-filled rows and stores nothing)
+  const uint32_t cta_rank = TWO_CTA ? cluster_ctarank() : 0u;
+  const int total_tiles = (TWO_CTA ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
+  const int work_first = TWO_CTA ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_stride = TWO_CTA ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp_idx == 0 && lane == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -164,16 +173,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], TWO_CTA ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // leader's: both CTAs' epilogues
     }
     fence_barrier_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (TWO_CTA) {
+      tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO_CTA) cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -183,23 +198,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       int s = 0;
       uint32_t ph = 0;
       const int TW = 1 << p.tw_log2, TH = GEMM_BLOCK_M >> p.tw_log2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = work_first; tile < total_tiles; tile += work_stride) {
         const int n_blk = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
+        int mt = (tile / p.n_tiles) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
         const int tx = mt % p.tiles_x;
         mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
-        const int b = mt / p.tiles_y;
+        const int b = mt / p.tiles_y;  // == p.B for the odd trailing M-tile of a pair: TMA zero-fills
         const int x0 = tx * TW + p.a_xoff, y0 = ty * TH;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int dy = p.num_taps == 9 ? tap / 3 - 1 : 0;
           const int dx = p.num_taps == 9 ? tap % 3 - 1 : 0;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-            tma_load_4d(smem_a + s * Cfg::A_BYTES, &p.tmA, &full_bar[s], kc * GEMM_BLOCK_K, x0 + dx, y0 + dy, b);
-            tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], (tap * p.kchunks + kc) * GEMM_BLOCK_K,
-                        n_blk * BLOCK_N);
+            if constexpr (TWO_CTA) {
+              // the leader's barrier collects the bytes of both CTAs; completion is signalled there
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+              tma_load_4d_2sm(smem_a + s * Cfg::A_BYTES, &p.tmA, &full_bar[s], kc * GEMM_BLOCK_K, x0 + dx, y0 + dy, b);
+              tma_load_2d_2sm(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], (tap * p.kchunks + kc) * GEMM_BLOCK_K,
+                              n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+              tma_load_4d(smem_a + s * Cfg::A_BYTES, &p.tmA, &full_bar[s], kc * GEMM_BLOCK_K, x0 + dx, y0 + dy, b);
+              tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], (tap * p.kchunks + kc) * GEMM_BLOCK_K,
+                          n_blk * BLOCK_N);
+            }
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -208,12 +231,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     __syncwarp();
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer =====================================
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, BLOCK_N, BF16, false, false);
+    if (cta_rank == 0 && elect_one()) {  // 2-CTA: only the leader issues MMAs (for both CTAs)
+      const uint32_t idesc = make_idesc_f16(TWO_CTA ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, BLOCK_N, BF16, false, false);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = work_first; tile < total_tiles; tile += work_stride, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
@@ -227,12 +250,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TWO_CTA) umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if constexpr (TWO_CTA) umma_commit_2sm(&empty_bar[s]);  // frees the stage in both CTAs
+          else umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        if constexpr (TWO_CTA) umma_commit_2sm(&tmem_full[as]);
+        else umma_commit(&tmem_full[as]);
       }
     }
     __syncwarp();
@@ -250,11 +276,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int r = q * 32 + lane;  // accumulator row (TMEM lane) owned by this thread
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = work_first; tile < total_tiles; tile += work_stride, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int n_blk = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
+      int mt = (tile / p.n_tiles) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
@@ -262,14 +288,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // output pixel of my row
       const int x = tx * TW + (r & (TW - 1));
       const int y = ty * TH + (r >> p.tw_log2);
-      const bool row_ok = (x < p.W) && (y < p.H);
+      const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
       const long long pix = ((long long)b * p.OH + (long long)y * p.so + p.oy) * p.OW + (long long)x * p.so + p.ox;
 
       // bias of this n-tile -> smem (zero beyond N / without bias); double-buffered by accumulator stage
       float* bs = bias_s + as * BLOCK_N;
       if (et < BLOCK_N) {
         const int n = n_blk * BLOCK_N + et;
-        bs[et] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + (long long)b * p.bias_bstride + n) : 0.0f;
+        bs[et] = (p.bias != nullptr && n < p.N && b < p.B) ? __ldg(p.bias + (long long)b * p.bias_bstride + n) : 0.0f;
       }
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
 
@@ -447,15 +473,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (TWO_CTA) mbar_arrive_leader(&tmem_empty[as]);
+        else mbar_arrive(&tmem_empty[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO_CTA) cluster_sync_all();  // the peer's smem / TMEM stay valid until both CTAs are done
+  else __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (TWO_CTA) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

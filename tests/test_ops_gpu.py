@@ -185,3 +185,58 @@ def test_attention_head_dim_32_with_window_bias():
     ref = (a.softmax(-1) @ v).transpose(1, 2).reshape(B * nW, N, Fd)
     rel, mx = rel_err(out, ref)
     assert rel < 1e-2, (rel, mx)
+
+
+# ---- shapes large enough for the 2-CTA (cta_group::2, 256 x 256 tile) kernel: >= 74 tile pairs
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,K,N,act", [(20001, 512, 768, 0), (12000, 1024, 1024, 1), (16300, 256, 512, 2)])
+def test_gemm_two_cta_pairs(M, K, N, act, dtype):
+    from gpu_util import conv_gemm, rel_err
+
+    A = _mk((1, 1, M, K), dtype, 41)
+    W = _mk((N, K), dtype, 42, K**-0.5)
+    bias = _mk((N,), torch.float32, 43)
+    out = conv_gemm(A, pack_linear(W), bias, act=act)
+    pre = A.float().reshape(M, K) @ W.float().t() + bias
+    ref = F.gelu(pre) if act == 1 else (F.relu(pre) if act == 2 else pre)
+    rel, mx = rel_err(out.reshape(M, N), ref)
+    assert rel < _tol(dtype), (rel, mx)
+    assert torch.isfinite(out.float()).all()
+
+
+def test_gemm_two_cta_f32_residual_inplace():
+    from gpu_util import rel_err
+    import ctypes as C
+    from muggled_dpt_b200 import _native as NN
+
+    M, K, N = 19999, 512, 1024
+    A = _mk((1, 1, M, K), torch.bfloat16, 44)
+    W = _mk((N, K), torch.bfloat16, 45, K**-0.5)
+    bias = _mk((N,), torch.float32, 46)
+    x = _mk((M, N), torch.float32, 47)
+    ref = x + A.float().reshape(M, K) @ W.float().t() + bias
+    Wp = pack_linear(W)
+    rc = NN.lib().dpt_op_conv_gemm(A.data_ptr(), Wp.data_ptr(), bias.data_ptr(), x.data_ptr(), x.data_ptr(), None, None,
+                                   1, 1, M, K, N, 1, 0, 0, 1, NN.DPT_BF16,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    NN.check(rc, None, "gemm")
+    torch.cuda.synchronize()
+    rel, mx = rel_err(x, ref)
+    assert rel < 1e-3, (rel, mx)
+
+
+def test_conv3x3_two_cta_pairs():
+    from gpu_util import conv_gemm, rel_err
+
+    B, H, W, C, N = 3, 144, 144, 64, 256   # 3 * 162 = 486 M-tiles
+    x = _mk((B, H, W, C), torch.bfloat16, 48)
+    w = _mk((N, C, 3, 3), torch.bfloat16, 49, (9 * C) ** -0.5)
+    bias = _mk((N,), torch.float32, 50)
+    a1 = _mk((B, H, W, N), torch.bfloat16, 51)
+    out, out_relu = conv_gemm(x, pack_conv(w), bias, add1=a1, want_relu=True, taps=9)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1) + a1.float()
+    rel, mx = rel_err(out, ref)
+    assert rel < 8e-3, (rel, mx)
+    assert torch.equal(out_relu, torch.relu(out))
