@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;  // single fp32 accumulator [128 x 64]
+  pdl_wait();                // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   // Register rebalancing (setmaxnreg is per warpgroup): the kernel launches at 128 registers/thread so that two CTAs
   // fit an SM; the producer/MMA warpgroup gives most of its registers back and the softmax warpgroup, which keeps a

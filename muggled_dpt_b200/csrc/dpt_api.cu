@@ -158,6 +158,44 @@ bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
   return true;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// cudaLaunchKernelEx with the programmatic-dependent-launch attribute (kernels launched through here call
+// pdl_wait() before reading anything a previous kernel wrote) and, optionally, a cluster of two CTAs.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool cluster2,
+                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 int pick_block_n(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
 template <int BN, int OUT_KIND, int ACT, bool BF16>
@@ -169,8 +207,8 @@ cudaError_t launch_gemm_inst(const GemmParams& p, int grid, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<BN, OUT_KIND, ACT, BF16><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, s>>>(p);
-  return cudaGetLastError();
+  return launch_ex(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16>, dim3((unsigned)grid), dim3(GEMM_THREADS),
+                   GemmCfg<BN>::SMEM_BYTES, s, false, p);
 }
 
 // 2-CTA (cta_group::2) variant: BLOCK_N = 256, launched as clusters of two CTAs
@@ -184,19 +222,7 @@ cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, p);
+  return launch_ex(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), smem, s, true, p);
 }
 
 template <bool BF16>
@@ -363,8 +389,7 @@ cudaError_t launch_attn_inst(const AttnParams& p, dim3 grid, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  attn_tc_kernel<HAS_BIAS, BF16, HD><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(p);
-  return cudaGetLastError();
+  return launch_ex(attn_tc_kernel<HAS_BIAS, BF16, HD>, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, s, false, p);
 }
 template <bool HAS_BIAS, int HD>
 cudaError_t launch_attn(const AttnParams& p, dim3 grid, cudaStream_t s) {
@@ -421,8 +446,10 @@ bool add_layernorm(Ctx& c, const float* x, const float* w, const float* b, void*
   c.add("layernorm:" + c.scope, 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
     const int rows_per_block = 8;
     const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
-    DISPATCH_T(is_bf16, (layernorm_kernel<T, float><<<grid, rows_per_block * 32, 0, s>>>(x, w, b, (T*)y, M, F, eps)));
-    return cudaGetLastError();
+    cudaError_t e;
+    DISPATCH_T(is_bf16, (e = launch_ex(layernorm_kernel<T, float>, dim3(grid), dim3(rows_per_block * 32), 0, s, false, x,
+                                       w, b, (T*)y, (long long)M, F, eps)));
+    return e;
   });
   return true;
 }
@@ -435,8 +462,10 @@ bool add_layernorm_h(Ctx& c, const void* x16, const float* w, const float* b, vo
   c.add("layernorm:" + c.scope, 0.0, (double)M * F * 4.0, [=](cudaStream_t s) {
     const int rows_per_block = 8;
     const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
-    DISPATCH_T(is_bf16, (layernorm_kernel<T, T><<<grid, rows_per_block * 32, 0, s>>>((const T*)x16, w, b, (T*)y, M, F, eps)));
-    return cudaGetLastError();
+    cudaError_t e;
+    DISPATCH_T(is_bf16, (e = launch_ex(layernorm_kernel<T, T>, dim3(grid), dim3(rows_per_block * 32), 0, s, false,
+                                       (const T*)x16, w, b, (T*)y, (long long)M, F, eps)));
+    return e;
   });
   return true;
 }
@@ -447,8 +476,9 @@ bool add_cast_to_half(Ctx& c, const float* x, void* y, long long n, const char* 
   const int is_bf16 = c.is_bf16, nsm = c.num_sms;
   c.add(std::string(label) + ":" + c.scope, 0.0, (double)n * 6.0, [=](cudaStream_t s) {
     const int grid = ew_grid(n / 4, 256, nsm);
-    DISPATCH_T(is_bf16, (cast_f32_kernel<T><<<grid, 256, 0, s>>>(x, (T*)y, n / 4)));
-    return cudaGetLastError();
+    cudaError_t e;
+    DISPATCH_T(is_bf16, (e = launch_ex(cast_f32_kernel<T>, dim3(grid), dim3(256), 0, s, false, x, (T*)y, (long long)(n / 4))));
+    return e;
   });
   return true;
 }
@@ -461,8 +491,10 @@ bool add_resize(Ctx& c, const void* in, void* out, int B, int IH, int IW, int OH
   c.add("resize:" + c.scope, 0.0, ((double)B * IH * IW + (double)B * OH * OW) * C * 2.0, [=](cudaStream_t s) {
     (void)nsm;
     const dim3 grid((unsigned)((OW * (C / 8) + 255) / 256), (unsigned)OH, (unsigned)B);
-    DISPATCH_T(is_bf16, (resize_bilinear_ac_kernel<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, B, IH, IW, OH, OW, C)));
-    return cudaGetLastError();
+    cudaError_t e;
+    DISPATCH_T(is_bf16, (e = launch_ex(resize_bilinear_ac_kernel<T>, grid, dim3(256), 0, s, false, (const T*)in, (T*)out, B,
+                                       IH, IW, OH, OW, C)));
+    return e;
   });
   return true;
 }
@@ -669,8 +701,10 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
         void* tp = taps[st];
         c.add("cast_tap:" + c.scope, 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
           const int grid = ew_grid(M * F / 4, 256, nsm);
-          DISPATCH_T(is_bf16, (cast_f32_kernel<T><<<grid, 256, 0, s>>>(x, (T*)tp, M * F / 4)));
-          return cudaGetLastError();
+          cudaError_t e;
+          DISPATCH_T(is_bf16, (e = launch_ex(cast_f32_kernel<T>, dim3(grid), dim3(256), 0, s, false, (const float*)x, (T*)tp,
+                                             (long long)(M * F / 4))));
+          return e;
         });
       }
     }

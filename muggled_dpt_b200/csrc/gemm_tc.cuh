@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();   // and the next kernel may do the same with ours
 
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cstdint>
+#include "ptx.cuh"
 
 namespace dpt {
 
@@ -136,6 +137,8 @@ template <typename T, typename TIN>
 __global__ void layernorm_kernel(const TIN* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia,
                                  T* __restrict__ y, long long M, int F, float eps) {
   constexpr int MAXV = 12;  // F <= 1536
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -193,6 +196,8 @@ template <typename T>
 __global__ void resize_bilinear_ac_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int IH, int IW, int OH,
                                           int OW, int C) {
   // grid = (ceil(OW * C/8 / blockDim), OH, B): one output row per (blockIdx.y, blockIdx.z), 32-bit index math only
+  pdl_wait();
+  pdl_launch_dependents();
   const int cv = C >> 3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= OW * cv) return;
@@ -236,6 +241,8 @@ __global__ void relu_copy_kernel(const T* __restrict__ in, T* __restrict__ out, 
 // fp32 -> 16-bit cast (BEiT taps: the encoder has no output norm), 4 elements per thread
 template <typename T>
 __global__ void cast_f32_kernel(const float* __restrict__ in, T* __restrict__ out, long long n4) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n4;
        idx += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(in)[idx];

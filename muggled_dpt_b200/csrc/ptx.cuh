@@ -28,6 +28,13 @@ DPT_DEVICE bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel in the stream drains; it must call
+// pdl_wait() before touching memory the previous kernel wrote. pdl_launch_dependents() lets the NEXT kernel do the same.
+DPT_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DPT_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
 // mbarrier
 
 DPT_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
