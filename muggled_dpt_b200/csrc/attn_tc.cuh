@@ -9,32 +9,49 @@
 // One CTA = one 128-row query tile of one (batch, head); two CTAs are co-resident per SM so one CTA's tensor-core work
 // overlaps the other's softmax. Warp roles: warps 0..3 softmax (one query row per thread, 208 registers after
 // setmaxnreg), warp 4 TMA producer, warp 5 MMA issuer (+TMEM alloc).
-//   S = Q K_j^T        tcgen05.mma M=128 N=128 K=64  -> TMEM cols [0,128)
+//   S = Q K_j^T        tcgen05.mma (SS) M=128 N=128 K=d  -> TMEM cols [0,128)
 //   softmax thread     reads its whole S row (128 fp32) into registers in ONE TMEM pass and releases S at once
 //                      (S_{j+1} is computed while P_j is still being exponentiated); exact row max; the stabiliser mu
 //                      only moves when the max grows by more than 2^8 ("lazy rescale"), so P <= 256 and the
-//                      accumulator rarely needs touching; P = exp2(S*c - mu) 16-bit -> swizzled smem
-//   O += P V_j         tcgen05.mma M=128 N=64 K=128 accumulating in TMEM cols [128,192) (V is the MN-major B operand,
-//                      straight from the TMA tile). On the rare rescale a warp multiplies its 32 accumulator rows by
-//                      exp2(mu_old - mu_new) through tcgen05.ld / tcgen05.st before P_j is published.
-// TMEM read traffic per kv step is one S tile (64 KB) - the SM's TMEM read port (64 B/clk) and the MUFU ex2 rate
-// (16/clk) both cost 1024 cycles per step, which is what bounds this kernel at d = 64.
+//                      accumulator rarely needs touching; P = exp2(S*c - mu), packed to 16 bits and written straight
+//                      back to TMEM cols [128,192) with tcgen05.st (row = lane, two kv columns per 32-bit column)
+//   O += P V_j         tcgen05.mma (TS: A = P from TMEM, B = V from smem, MN-major, straight from the TMA tile)
+//                      M=128 N=64 K=128 accumulating in TMEM cols [192,256). On the rare rescale a warp multiplies its
+//                      32 accumulator rows by exp2(mu_old - mu_new) through tcgen05.ld / tcgen05.st first.
+// Keeping P out of shared memory matters: with P staged in smem the tile's smem traffic (STS P 32 KB + MMA reads of
+// Q,K 32 KB and P,V 48 KB + TMA writes 32 KB = 144 KB per kv step, ~1150 clk at 128 B/clk) exceeded the MUFU time
+// (16384 ex2 / 16 per clk = 1024 clk) that should bound this kernel at d = 64; P in TMEM takes 64 KB of that away.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "ptx.cuh"
+#include <type_traits>
 #include "gemm_tc.cuh"  // pack2
 
 namespace dpt {
+
+// -DATT_TRACE (tools/attn_trace.py, never in the shipped library): lane 0 of each softmax warp of one CTA stamps
+// clock64 at the phase boundaries of every kv step; `dep` ties the stamp to the last value the phase produced.
+#ifdef ATT_TRACE
+__device__ long long g_att_trace[4][16][10];
+#define ATT_T(ph, dep)                                                                        \
+  if (trace_on && j < 16) {                                                                   \
+    long long t_;                                                                             \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(dep) : "memory");                  \
+    g_att_trace[q][j][ph] = t_;                                                               \
+  }
+#else
+#define ATT_T(ph, dep)
+#endif
 
 constexpr int ATT_THREADS = 256;  // warpgroup 0 = softmax (4 warps), warpgroup 1 = TMA producer, MMA issuer, 2 idle
 constexpr int ATT_BM = 128;   // query rows per CTA
 constexpr int ATT_BN = 128;   // kv rows per step
 constexpr int ATT_D = 64;
-constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_KV_STAGES = 3;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-// smem: Q | K[2] | V[2] | P (2 chunks) | barriers
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES + 2) + 256;
+// smem: Q | K[stages] | V[stages] | barriers
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES) + 256;
 constexpr int ATT_TMEM_COLS = 256;
 
 struct __align__(64) AttnParams {
@@ -93,18 +110,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;
-  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_TILE_BYTES);
+  constexpr int ST = ATT_KV_STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * ATT_TILE_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_ready = bars + 10;
-  uint64_t* o_full = bars + 11;   // [2]
-  uint64_t* s_free = bars + 13;   // S_j has been read out of TMEM for the last time (S_{j+1} may overwrite it)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* k_full = bars + 1;           // [ST]
+  uint64_t* k_empty = k_full + ST;       // [ST]
+  uint64_t* v_full = k_empty + ST;       // [ST]
+  uint64_t* v_empty = v_full + ST;       // [ST]
+  uint64_t* s_full = v_empty + ST;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* o_full = s_full + 2;         // [2]
+  uint64_t* s_free = s_full + 4;         // S_j has been read out of TMEM for the last time (S_{j+1} may overwrite it)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 5);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,13 +137,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     }
     prefetch_tmap(&p.tmQKV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&o_full[i], 1);
     }
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(s_free, 128);
@@ -141,7 +159,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;  // single fp32 accumulator [128 x 64]
+  const uint32_t tmem_P = tmem_base + 128;  // 16-bit P [128 x 128] = 64 columns
+  const uint32_t tmem_O = tmem_base + 192;  // single fp32 accumulator [128 x 64]
   pdl_wait();                // everything above overlapped the previous kernel's tail
   pdl_launch_dependents();
 
@@ -156,8 +175,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_3d(sQ, &p.tmQKV, q_full, h * HD, q0, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int s = j % ST;
+        const uint32_t ph = (j / ST) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
         tma_load_3d(sK + s * ATT_TILE_BYTES, &p.tmQKV, &k_full[s], p.F + h * HD, j * ATT_BN, b);
@@ -173,8 +192,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       const uint32_t idesc_s = make_idesc_f16(128, ATT_BN, BF16, false, false);
       const uint32_t idesc_o = make_idesc_f16(128, ATT_D, BF16, false, true);  // V: MN-major B operand
       const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ));
-      const uint64_t p_desc0 = make_smem_desc_sw128(smem_u32(sP));
-      const uint64_t p_desc1 = make_smem_desc_sw128(smem_u32(sP + ATT_TILE_BYTES));
       mbar_wait(q_full, 0);
       // S_0
       mbar_wait(&k_full[0], 0);
@@ -187,12 +204,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
         umma_commit(s_full);
       }
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int s = j % ST;
+        const uint32_t ph = (j / ST) & 1;
         // S_{j+1} as soon as S_j has been read for the last time (the softmax warps are still exponentiating)
         if (j + 1 < n_kv) {
-          const int s1 = (j + 1) & 1;
-          const uint32_t ph1 = ((j + 1) >> 1) & 1;
+          const int s1 = (j + 1) % ST;
+          const uint32_t ph1 = ((j + 1) / ST) & 1;
           mbar_wait(s_free, j & 1);
           mbar_wait(&k_full[s1], ph1);
           tc_fence_after();
@@ -202,16 +219,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
           umma_commit(&k_empty[s1]);
           umma_commit(s_full);
         }
-        // P_j is in smem
+        // P_j is in TMEM
         mbar_wait(p_ready, j & 1);
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
         const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV + s * ATT_TILE_BYTES));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t a_desc = (kk < 4 ? p_desc0 : p_desc1) + 2 * (kk & 3);
-          // V rows kk*16.. : 16 rows * 128 B = 2048 B -> +128 in the (addr >> 4) field
-          umma_f16_ss(tmem_O, a_desc, v_desc + 128 * kk, idesc_o, (j | kk) != 0);
+          // P columns kk*16.. = 8 TMEM columns; V rows kk*16.. : 16 rows * 128 B = 2048 B -> +128 in the (addr >> 4) field
+          umma_f16_ts(tmem_O, tmem_P + 8 * kk, v_desc + 128 * kk, idesc_o, (j | kk) != 0);
         }
         umma_commit(&v_empty[s]);
         umma_commit(&o_full[j & 1]);
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     constexpr int is_bf16 = BF16 ? 1 : 0;
     const float c = p.scale_log2;
     const float2 c2 = make_float2(c, c);
-    float mu = -INFINITY;  // stabiliser in exp2 units (score * scale * log2e [+ bias * log2e]); >= row max - 8
+    float mu = 0.0f;       // stabiliser in exp2 units (score * scale * log2e [+ bias * log2e]); >= row max - 8
     float2 l2[4];          // row sum of P, four independent packed accumulators
 #pragma unroll
     for (int i = 0; i < 4; ++i) l2[i] = make_float2(0.0f, 0.0f);
@@ -242,11 +258,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     const uint32_t s_addr = tmem_S + lane_addr;
     const uint32_t o_addr = tmem_O + lane_addr;
 
-    for (int j = 0; j < n_kv; ++j) {
+    const uint32_t p_addr = tmem_P + lane_addr;
+
+    // one kv step; MASKED = this step holds columns >= N (only the last one can)
+#ifdef ATT_TRACE
+    const bool trace_on = lane == 0 && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 1;
+#endif
+    auto step = [&](const int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      ATT_T(0, j);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      ATT_T(1, j);
       const int kv0 = j * ATT_BN;
-      const bool tail = (kv0 + ATT_BN > p.N);
       // ---- the whole S row -> registers, then S is free for the next QK^T
       uint32_t sv[4][32];
 #pragma unroll
@@ -255,6 +279,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       for (int ci = 0; ci < 4; ++ci) tmem_ld_wait_dep(sv[ci]);
       tc_fence_before();
       mbar_arrive(s_free);
+      ATT_T(2, sv[3][31]);
       if constexpr (HAS_BIAS) {
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
@@ -264,7 +289,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
           for (int i = 0; i < 32; ++i) sv[ci][i] = __float_as_uint(fmaf(__uint_as_float(sv[ci][i]), c, bf[i]));
         }
       }
-      if (tail) {
+      if constexpr (MASKED) {
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
@@ -283,11 +308,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       float m_tile = fmaxf(fmaxf(m_t[0], m_t[1]), fmaxf(m_t[2], m_t[3]));
       if constexpr (!HAS_BIAS) m_tile *= c;  // max(c*s) = c*max(s), c > 0
       // ---- lazy rescale decision: move the stabiliser only when the row max outgrew it by more than 2^8
-      const bool need = m_tile > mu + 8.0f;  // always true for j == 0 (mu = -inf)
+      const bool need = m_tile > mu + 8.0f;
       const bool warp_rescale = (j > 0) && __any_sync(0xffffffffu, need);
       float beta = 1.0f;
       if (j == 0) {
-        mu = m_tile;
+        mu = m_tile;  // finite: the first step always holds at least one unmasked column
       } else if (warp_rescale) {
         const float mu_new = need ? m_tile : mu;
         beta = ex2_approx(mu - mu_new);  // 1 for rows that keep their stabiliser
@@ -298,6 +323,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       }
       // ---- P = exp2(s*c - mu) (<= 256) in place, in three sweeps (scale/shift, ex2, sum + pack) so that the MUFU
       //      results are consumed long after they are issued; kept packed in registers while P_{j-1} V_{j-1} finishes
+      ATT_T(3, __float_as_uint(mu));
       const float2 neg_mu2 = make_float2(-mu, -mu);
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
@@ -311,42 +337,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
           sv[ci][i + 1] = __float_as_uint(e.y);
         }
       }
+      ATT_T(4, sv[3][31]);
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) sv[ci][i] = __float_as_uint(ex2_approx(__uint_as_float(sv[ci][i])));  // ex2(-inf) = 0
       }
-      uint32_t pk[64];
+      ATT_T(5, sv[3][31]);
+      uint32_t pk[2][32];  // 128 kv columns, two per register: the K-major A operand of P@V, 64 TMEM columns
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 pf = make_float2(__uint_as_float(sv[ci][2 * i]), __uint_as_float(sv[ci][2 * i + 1]));
           l2[i & 3] = __fadd2_rn(l2[i & 3], pf);
-          pk[ci * 16 + i] = pack2(pf.x, pf.y, is_bf16);
+          pk[ci >> 1][(ci & 1) * 16 + i] = pack2(pf.x, pf.y, is_bf16);
         }
       }
-      // ---- the previous P@V must be complete: it reads the P buffer and writes the accumulator
+      ATT_T(6, pk[1][31]);
+      // ---- the previous P@V must be complete: it reads P and writes the accumulator
       if (j > 0) {
         mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
         if (warp_rescale) rescale_accumulator(o_addr, beta);  // out of line: rare
       }
-      // ---- 16-bit P -> swizzled smem
-#pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        uint8_t* chunk_base = sP + (ci >> 1) * ATT_TILE_BYTES + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte smem chunk
-          const int phys = (((ci & 1) * 4) + g) ^ (r & 7);
-          *reinterpret_cast<uint4*>(chunk_base + phys * 16) =
-              make_uint4(pk[ci * 16 + g * 4 + 0], pk[ci * 16 + g * 4 + 1], pk[ci * 16 + g * 4 + 2], pk[ci * 16 + g * 4 + 3]);
-        }
-      }
-      // make P visible to the tensor core (async proxy); P_j V_j is issued after this
-      fence_proxy_async_smem();
+      ATT_T(7, j);
+      // ---- 16-bit P -> TMEM; P_j V_j is issued once all four warps have arrived
+      tmem_st32(p_addr, pk[0]);
+      tmem_st32(p_addr + 32, pk[1]);
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(p_ready);
-    }
+      ATT_T(8, j);
+    };
+    for (int j = 0; j + 1 < n_kv; ++j) step(j, std::false_type{});
+    step(n_kv - 1, std::true_type{});
     // ---- epilogue: O / l
     {
       const int j = n_kv - 1;

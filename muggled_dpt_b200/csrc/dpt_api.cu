@@ -257,6 +257,8 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, bool two_cta, cud
   return p.is_bf16 ? launch_gemm_dt<true>(p, bn, grid, s) : launch_gemm_dt<false>(p, bn, grid, s);
 }
 
+constexpr double kCostPair = 1.00, kCost256 = 1.08, kCost128 = 0.60;
+
 bool two_cta_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -264,6 +266,38 @@ bool two_cta_enabled() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+
+// DPT_GEMM_MODE (tuning aid): 0 = cost model (default), 1 = CTA pairs whenever they fill half the machine,
+// 2 = 128x256 single-CTA tiles, 3 = 128x128 single-CTA tiles. Modes 1-3 only affect GEMMs with N > 128.
+int gemm_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_GEMM_MODE");
+    v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+  }
+  return v;
+}
+
+// Tile choice for wide GEMMs (N > 128). Tiles are dealt round-robin to a persistent grid, so a launch costs
+// rounds x time-per-tile; the relative tile costs below were fitted to per-launch timings on B200.
+struct TileChoice { int bn; bool two_cta; };
+TileChoice choose_tile(long long m_tiles, int N, int num_sms) {
+  const long long pairs = (m_tiles + 1) / 2;
+  const int nt256 = (N + 255) / 256, nt128 = (N + 127) / 128;
+  const bool pairs_ok = two_cta_enabled() && pairs * nt256 >= num_sms / 2;
+  switch (gemm_mode()) {
+    case 1: return {256, pairs_ok};
+    case 2: return {256, false};
+    case 3: return {128, false};
+    default: break;
+  }
+  auto rounds = [](long long tiles, int slots) { return (double)((tiles + slots - 1) / slots); };
+  const double c_pair = pairs_ok ? rounds(pairs * nt256, num_sms / 2) * kCostPair : 1e30;
+  const double c_256 = rounds(m_tiles * nt256, num_sms) * kCost256;
+  const double c_128 = rounds(m_tiles * nt128, num_sms) * kCost128;
+  if (c_pair <= c_256 && c_pair <= c_128) return {256, true};
+  return c_256 <= c_128 ? TileChoice{256, false} : TileChoice{128, false};
 }
 
 // Description of one spatial GEMM (see gemm_tc.cuh).
@@ -317,8 +351,15 @@ bool add_gemm(Ctx& c, GemmOp op) {
     if (best_tiles < 0 || t < best_tiles) { best_tiles = t; best_log2 = l2; }
   }
   const int TW = 1 << best_log2, TH = 128 >> best_log2;
-  const int bn = op.out_kind == OUT_HEAD ? 32 : pick_block_n(op.N);
   if (op.out_kind == OUT_HEAD && op.N != 32) return c.fail("gemm: head mode needs N == 32");
+  const long long m_tiles_all = (long long)op.B * ((op.W + TW - 1) / TW) * ((op.H + TH - 1) / TH);
+  int bn = op.out_kind == OUT_HEAD ? 32 : pick_block_n(op.N);
+  bool two_cta = false;
+  if (bn == 256 && op.out_kind != OUT_HEAD) {
+    const TileChoice tc = choose_tile(m_tiles_all, op.N, c.num_sms);
+    bn = tc.bn;
+    two_cta = tc.two_cta;
+  }
 
   {
     uint64_t dims[4] = {(uint64_t)op.C, (uint64_t)op.Wt, (uint64_t)op.Ht, (uint64_t)op.B};
@@ -327,10 +368,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
     if (!make_tmap(&p.tmA, op.A, 4, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
   }
   // CTA pairs (cta_group::2, 256 x 256 tiles) when the problem is wide and tall enough to fill the machine with pairs
-  const long long m_tiles_all = (long long)op.B * ((op.W + TW - 1) / TW) * ((op.H + TH - 1) / TH);
   const int n_tiles_all = (op.N + bn - 1) / bn;
-  const bool two_cta = two_cta_enabled() && bn == 256 && op.out_kind != OUT_HEAD &&
-                       ((m_tiles_all + 1) / 2) * n_tiles_all >= c.num_sms / 2;
   {
     const uint64_t ktot = (uint64_t)op.taps * op.kpad;
     uint64_t dims[2] = {ktot, (uint64_t)op.N};
@@ -1515,3 +1553,10 @@ int dpt_op_resize_bilinear(const void* in, void* out, int B, int IH, int IW, int
 }
 
 }  // extern "C"
+
+#ifdef ATT_TRACE
+// trace build only (tools/attn_trace.py): copies the per-phase clock stamps of attn_tc_kernel to the host
+extern "C" int dpt_debug_attn_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, dpt::g_att_trace, sizeof(long long) * 4 * 16 * 10);
+}
+#endif

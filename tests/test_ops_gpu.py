@@ -118,7 +118,8 @@ def test_conv3x3_addends_and_relu_copy():
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (2, 257, 2), (1, 1297, 3), (2, 100, 1)])
+@pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (2, 257, 2), (1, 1297, 3), (2, 100, 1), (1, 17, 1), (2, 64, 2),
+                                       (3, 65, 1), (1, 193, 2)])
 def test_attention(B, N, heads, dtype):
     from gpu_util import attention, rel_err
 
@@ -129,6 +130,22 @@ def test_attention(B, N, heads, dtype):
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, Fd)
     rel, mx = rel_err(out, ref)
     assert rel < (1e-2 if dtype == torch.bfloat16 else 3e-3), (rel, mx)  # P is rounded to 16 bits before P@V
+
+
+@pytest.mark.parametrize("N", [40, 333, 1297])
+def test_attention_large_logits(N):
+    """logits with a spread of tens of exp2 units: the stabiliser moves (lazy rescale) and the two split-KV halves of
+    a row end up with very different maxima before they are merged"""
+    from gpu_util import attention, rel_err
+
+    B, heads = 2, 2
+    Fd = heads * 64
+    qkv = (_mk((B, N, 3 * Fd), torch.bfloat16, 31).float() * 3.0).to(torch.bfloat16)
+    out = attention(qkv, heads, 0.125)
+    q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, Fd)
+    rel, mx = rel_err(out, ref)
+    assert rel < 1e-2, (rel, mx)
 
 
 def test_attention_with_bias():
