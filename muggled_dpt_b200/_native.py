@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdpt_b200.so")
+# DPT_B200_LIB: an alternative build of the same library (kernel A/B experiments under tools/), never a fallback
+LIB_PATH = os.environ.get("DPT_B200_LIB") or os.path.join(_HERE, "lib", "libdpt_b200.so")
 
 DPT_F16, DPT_BF16, DPT_F32 = 0, 1, 2
 VARIANT_DINOV2, VARIANT_BEIT, VARIANT_SWINV2 = 0, 1, 2

@@ -44,6 +44,9 @@ __device__ long long g_att_trace[4][16][10];
 #define ATT_T(ph, dep)
 #endif
 
+#ifndef ATT_POLY_PAIRS
+#define ATT_POLY_PAIRS 2  // of every 8 element pairs, how many take exp2 on the FMA pipe (ex2_poly2) instead of the MUFU
+#endif
 constexpr int ATT_THREADS = 256;  // warpgroup 0 = softmax (4 warps), warpgroup 1 = TMA producer, MMA issuer, 2 idle
 constexpr int ATT_BM = 128;   // query rows per CTA
 constexpr int ATT_BN = 128;   // kv rows per step
@@ -129,6 +132,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int n_kv = (p.N + ATT_BN - 1) / ATT_BN;
+  // The last kv step holds N - (n_kv-1)*128 rows: only its first `last_chunks` 32-column chunks are computed at all
+  // (S = Q K^T at N = 32*last_chunks, exponentials on those chunks only, P@V at K = 32*last_chunks).
+  const int last_chunks = (p.N - (n_kv - 1) * ATT_BN + 31) >> 5;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_f16(128, ATT_BN, BF16, false, false);
+      const uint32_t idesc_s_last = make_idesc_f16(128, 32 * last_chunks, BF16, false, false);  // tail: fewer kv columns
       const uint32_t idesc_o = make_idesc_f16(128, ATT_D, BF16, false, true);  // V: MN-major B operand
       const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ));
       mbar_wait(q_full, 0);
@@ -199,7 +206,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       {
         const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK));
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, n_kv == 1 ? idesc_s_last : idesc_s, k != 0);
         umma_commit(&k_empty[0]);
         umma_commit(s_full);
       }
@@ -215,7 +223,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
           tc_fence_after();
           const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK + s1 * ATT_TILE_BYTES));
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_f16_ss(tmem_S, q_desc + 2 * k, k_desc + 2 * k, j + 2 == n_kv ? idesc_s_last : idesc_s, k != 0);
           umma_commit(&k_empty[s1]);
           umma_commit(s_full);
         }
@@ -224,10 +233,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
         const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV + s * ATT_TILE_BYTES));
+        const int kk_end = (j + 1 == n_kv) ? 2 * last_chunks : 8;  // tail: only the 32-column chunks that hold kv rows
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           // P columns kk*16.. = 8 TMEM columns; V rows kk*16.. : 16 rows * 128 B = 2048 B -> +128 in the (addr >> 4) field
-          umma_f16_ts(tmem_O, tmem_P + 8 * kk, v_desc + 128 * kk, idesc_o, (j | kk) != 0);
+          if (kk < kk_end) umma_f16_ts(tmem_O, tmem_P + 8 * kk, v_desc + 128 * kk, idesc_o, (j | kk) != 0);
         }
         umma_commit(&v_empty[s]);
         umma_commit(&o_full[j & 1]);
@@ -264,25 +274,31 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
 #ifdef ATT_TRACE
     const bool trace_on = lane == 0 && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 1;
 #endif
-    auto step = [&](const int j, auto masked_tag) {
-      constexpr bool MASKED = decltype(masked_tag)::value;
+    auto step = [&](const int j, auto nch_tag) {
+      constexpr int NCH_TAG = decltype(nch_tag)::value;  // 0: full unmasked step; 1..4: tail step with that many chunks
+      constexpr bool MASKED = NCH_TAG != 0;
       ATT_T(0, j);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       ATT_T(1, j);
       const int kv0 = j * ATT_BN;
       // ---- the whole S row -> registers, then S is free for the next QK^T
+      // MASKED step: chunks [nch, 4) hold no kv rows at all - never loaded, exponentiated or fed to P@V
+      constexpr int nch = MASKED ? NCH_TAG : 4;
       uint32_t sv[4][32];
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) tmem_ld32(s_addr + ci * 32, sv[ci]);
+      for (int ci = 0; ci < 4; ++ci)
+        if (!MASKED || ci < nch) tmem_ld32(s_addr + ci * 32, sv[ci]);
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) tmem_ld_wait_dep(sv[ci]);
+      for (int ci = 0; ci < 4; ++ci)
+        if (!MASKED || ci < nch) tmem_ld_wait_dep(sv[ci]);
       tc_fence_before();
       mbar_arrive(s_free);
       ATT_T(2, sv[3][31]);
       if constexpr (HAS_BIAS) {
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
+          if (MASKED && ci >= nch) continue;
           float bf[32];
           load_bias32(bias_row + kv0 + ci * 32, bf, is_bf16);
 #pragma unroll
@@ -291,20 +307,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       }
       if constexpr (MASKED) {
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci)
+        for (int ci = 0; ci < 4; ++ci) {
+          if (ci >= nch) continue;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (kv0 + ci * 32 + i >= p.N) sv[ci][i] = 0xff800000u;  // -inf
+        }
       }
       // ---- exact row max (four independent chains)
       float m_t[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci)
+      for (int ci = 0; ci < 4; ++ci) {
+        if (MASKED && ci >= nch) continue;
 #pragma unroll
         for (int i = 0; i < 32; i += 8)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             m_t[k] = fmaxf(m_t[k], fmaxf(__uint_as_float(sv[ci][i + 2 * k]), __uint_as_float(sv[ci][i + 2 * k + 1])));
+      }
       float m_tile = fmaxf(fmaxf(m_t[0], m_t[1]), fmaxf(m_t[2], m_t[3]));
       if constexpr (!HAS_BIAS) m_tile *= c;  // max(c*s) = c*max(s), c > 0
       // ---- lazy rescale decision: move the stabiliser only when the row max outgrew it by more than 2^8
@@ -327,6 +347,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       const float2 neg_mu2 = make_float2(-mu, -mu);
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
+        if (MASKED && ci >= nch) continue;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float2 x = make_float2(__uint_as_float(sv[ci][i]), __uint_as_float(sv[ci][i + 1]));
@@ -340,13 +361,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       ATT_T(4, sv[3][31]);
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
+        if (MASKED && ci >= nch) continue;
+        // of every 8 pairs, the last ATT_POLY_PAIRS go to the FMA-pipe polynomial, the rest to the MUFU
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[ci][i] = __float_as_uint(ex2_approx(__uint_as_float(sv[ci][i])));  // ex2(-inf) = 0
+        for (int i = 0; i < 32; i += 2) {
+          if (((i >> 1) & 7) >= 8 - ATT_POLY_PAIRS) {
+            const float2 e = ex2_poly2<BF16 ? 3 : 4>(make_float2(__uint_as_float(sv[ci][i]), __uint_as_float(sv[ci][i + 1])));
+            sv[ci][i] = __float_as_uint(e.x);
+            sv[ci][i + 1] = __float_as_uint(e.y);
+          } else {
+            sv[ci][i] = __float_as_uint(ex2_approx(__uint_as_float(sv[ci][i])));  // ex2(-inf) = 0
+            sv[ci][i + 1] = __float_as_uint(ex2_approx(__uint_as_float(sv[ci][i + 1])));
+          }
+        }
       }
       ATT_T(5, sv[3][31]);
       uint32_t pk[2][32];  // 128 kv columns, two per register: the K-major A operand of P@V, 64 TMEM columns
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
+        if (MASKED && ci >= nch) {  // never read by the K = 32*nch P@V
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[ci >> 1][(ci & 1) * 16 + i] = 0u;
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 pf = make_float2(__uint_as_float(sv[ci][2 * i]), __uint_as_float(sv[ci][2 * i + 1]));
@@ -364,14 +401,30 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       ATT_T(7, j);
       // ---- 16-bit P -> TMEM; P_j V_j is issued once all four warps have arrived
       tmem_st32(p_addr, pk[0]);
-      tmem_st32(p_addr + 32, pk[1]);
+      if (!MASKED || nch > 2) tmem_st32(p_addr + 32, pk[1]);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
       ATT_T(8, j);
     };
-    for (int j = 0; j + 1 < n_kv; ++j) step(j, std::false_type{});
-    step(n_kv - 1, std::true_type{});
+    if (q0 + q * 32 >= p.N) {
+      // All 32 query rows of this warp lie past N (tail q tile): no softmax work, only the barrier protocol, in
+      // lockstep with the live warps (S_j produced -> released; P@V_{j-1} done -> "P_j ready"). The accumulator rows
+      // of this warp take whatever the P columns of TMEM happen to hold and are never stored.
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full, j & 1);
+        mbar_arrive(s_free);
+        if (j > 0) mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        mbar_arrive(p_ready);
+      }
+    } else {
+    for (int j = 0; j + 1 < n_kv; ++j) step(j, std::integral_constant<int, 0>{});
+    switch (last_chunks) {
+      case 1: step(n_kv - 1, std::integral_constant<int, 1>{}); break;
+      case 2: step(n_kv - 1, std::integral_constant<int, 2>{}); break;
+      case 3: step(n_kv - 1, std::integral_constant<int, 3>{}); break;
+      default: step(n_kv - 1, std::integral_constant<int, 4>{}); break;
+    }
     // ---- epilogue: O / l
     {
       const int j = n_kv - 1;
@@ -397,6 +450,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
           *reinterpret_cast<uint4*>(orow + 8 * ch) = o;
         }
       }
+    }
     }
   }
 

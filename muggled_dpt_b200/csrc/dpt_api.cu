@@ -528,7 +528,7 @@ bool add_resize(Ctx& c, const void* in, void* out, int B, int IH, int IW, int OH
   const int nsm = c.num_sms;
   c.add("resize:" + c.scope, 0.0, ((double)B * IH * IW + (double)B * OH * OW) * C * 2.0, [=](cudaStream_t s) {
     (void)nsm;
-    const dim3 grid((unsigned)((OW * (C / 8) + 255) / 256), (unsigned)OH, (unsigned)B);
+    const dim3 grid((unsigned)((OW * (C / 8) + 255) / 256), (unsigned)((OH + RESIZE_ROWS - 1) / RESIZE_ROWS), (unsigned)B);
     cudaError_t e;
     DISPATCH_T(is_bf16, (e = launch_ex(resize_bilinear_ac_kernel<T>, grid, dim3(256), 0, s, false, (const T*)in, (T*)out, B,
                                        IH, IW, OH, OW, C)));
