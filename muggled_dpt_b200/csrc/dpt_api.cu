@@ -198,24 +198,28 @@ cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
 
 int pick_block_n(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
-template <int BN, int OUT_KIND, int ACT, bool BF16>
+// the residual-prefetch variant of the fp32-output kernels (gemm_tc.cuh RESPF) is used for short K loops
+bool use_respf(const GemmParams& p) { return p.out_kind == OUT_F32 && p.add1 != nullptr && p.num_taps * p.kchunks <= 32; }
+
+template <int BN, int OUT_KIND, int ACT, bool BF16, bool RESPF = false>
 cudaError_t launch_gemm_inst(const GemmParams& p, int grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16, false, RESPF>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<BN, false, RESPF>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_ex(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16>, dim3((unsigned)grid), dim3(GEMM_THREADS),
-                   GemmCfg<BN>::SMEM_BYTES, s, false, p);
+  return launch_ex(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16, false, RESPF>, dim3((unsigned)grid), dim3(GEMM_THREADS),
+                   GemmCfg<BN, false, RESPF>::SMEM_BYTES, s, false, p);
 }
 
 // 2-CTA (cta_group::2) variant: BLOCK_N = 256, launched as clusters of two CTAs
-template <int OUT_KIND, int ACT, bool BF16>
+template <int OUT_KIND, int ACT, bool BF16, bool RESPF = false>
 cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<256, OUT_KIND, ACT, BF16, true>;
-  constexpr int smem = GemmCfg<256, true>::SMEM_BYTES;
+  auto kern = gemm_tc_kernel<256, OUT_KIND, ACT, BF16, true, RESPF>;
+  constexpr int smem = GemmCfg<256, true, RESPF>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -227,7 +231,9 @@ cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
 
 template <bool BF16>
 cudaError_t launch_gemm2_dt(const GemmParams& p, int grid, cudaStream_t s) {
-  if (p.out_kind == OUT_F32) return launch_gemm2_inst<OUT_F32, ACT_NONE, BF16>(p, grid, s);
+  if (p.out_kind == OUT_F32)
+    return use_respf(p) ? launch_gemm2_inst<OUT_F32, ACT_NONE, BF16, true>(p, grid, s)
+                        : launch_gemm2_inst<OUT_F32, ACT_NONE, BF16>(p, grid, s);
   if (p.act == ACT_GELU) return launch_gemm2_inst<OUT_HALF, ACT_GELU, BF16>(p, grid, s);
   if (p.act == ACT_RELU) return launch_gemm2_inst<OUT_HALF, ACT_RELU, BF16>(p, grid, s);
   return launch_gemm2_inst<OUT_HALF, ACT_NONE, BF16>(p, grid, s);
@@ -235,7 +241,9 @@ cudaError_t launch_gemm2_dt(const GemmParams& p, int grid, cudaStream_t s) {
 
 template <int BN, bool BF16>
 cudaError_t launch_gemm_bn(const GemmParams& p, int grid, cudaStream_t s) {
-  if (p.out_kind == OUT_F32) return launch_gemm_inst<BN, OUT_F32, ACT_NONE, BF16>(p, grid, s);
+  if (p.out_kind == OUT_F32)
+    return use_respf(p) ? launch_gemm_inst<BN, OUT_F32, ACT_NONE, BF16, true>(p, grid, s)
+                        : launch_gemm_inst<BN, OUT_F32, ACT_NONE, BF16>(p, grid, s);
   if (p.act == ACT_GELU) return launch_gemm_inst<BN, OUT_HALF, ACT_GELU, BF16>(p, grid, s);
   if (p.act == ACT_RELU) return launch_gemm_inst<BN, OUT_HALF, ACT_RELU, BF16>(p, grid, s);
   return launch_gemm_inst<BN, OUT_HALF, ACT_NONE, BF16>(p, grid, s);
@@ -321,6 +329,14 @@ struct GemmOp {
   long long ld_add2 = 0;
   void* out2_relu = nullptr;
   long long ld_out2 = 0;
+  // folded LayerNorm (gemm_tc.cuh): consumer side reads row statistics, producer side (OUT_F32) writes them
+  const float* ln_stats = nullptr;    // [rows, ln_parts, 2]
+  int ln_parts = 0;
+  const float* ln_colsum = nullptr;   // [N]
+  float ln_eps = 0.f;
+  float* stats_out = nullptr;         // [rows, *stats_parts, 2]; room for 2 * ceil(N / 64) parts per row
+  int* stats_parts = nullptr;         // receives the number of parts this GEMM writes per row
+  void* out16 = nullptr;              // 16-bit copy of the fp32 output
   const float* head_w = nullptr;      // host pointer to 32 floats (OUT_HEAD)
   float head_b = 0.f;
   int head_act = ACT_RELU;
@@ -396,6 +412,16 @@ bool add_gemm(Ctx& c, GemmOp op) {
   p.add1 = op.add1; p.ld_add1 = op.ld_add1 ? op.ld_add1 : op.ldo;
   p.add2 = op.add2; p.ld_add2 = op.ld_add2 ? op.ld_add2 : op.ldo;
   p.out2_relu = op.out2_relu; p.ld_out2 = op.ld_out2 ? op.ld_out2 : op.ldo;
+  if (op.ln_stats != nullptr) {
+    if (op.ln_colsum == nullptr || op.ln_parts <= 0 || (op.ln_parts & 1) || op.N < 32) return c.fail("gemm: folded LayerNorm needs colsum / parts");
+    p.ln_stats = op.ln_stats; p.ln_parts = op.ln_parts; p.ln_colsum = op.ln_colsum;
+    p.ln_inv_f = 1.0f / (float)op.C; p.ln_eps = op.ln_eps;
+  }
+  if (op.stats_out != nullptr) {
+    if (op.out_kind != OUT_F32 || bn < 64 || op.stats_parts == nullptr) return c.fail("gemm: row statistics need an fp32 output and BLOCK_N >= 64");
+    p.stats_out = op.stats_out; p.stats_parts = 2 * p.n_tiles; *op.stats_parts = p.stats_parts;
+    p.out16 = op.out16; p.ld_out16 = op.ldo;
+  }
   if (op.head_w) memcpy(p.head_w, op.head_w, 32 * sizeof(float));
   p.head_b = op.head_b;
   p.head_act = op.head_act;
@@ -412,6 +438,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
     if (op.add1) bytes += pix * op.N * osz;
     if (op.add2) bytes += pix * op.N * 2.0;
     if (op.out2_relu) bytes += pix * op.N * 2.0;
+    if (op.out16) bytes += pix * op.N * 2.0;
     c.add(std::string(two_cta ? "gemm256x2" : "gemm" + std::to_string(bn)) + ":" + c.scope + op.label, flops, bytes,
           [p, bn, grid, two_cta](cudaStream_t s) { return launch_gemm(p, bn, grid, two_cta, s); });
   }
@@ -627,7 +654,9 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
   const size_t mk = c.ar.mark();
   float* pos = (float*)c.ar.alloc((size_t)N * F * 4);
   float* x = (float*)c.ar.alloc((size_t)M * F * 4);
-  void* ln = c.ar.alloc((size_t)M * F * 2);
+  void* ln = c.ar.alloc((size_t)M * F * 2);  // 16-bit copy of the residual stream (A operand of qkv / fc1)
+  float* stats = (float*)c.ar.alloc((size_t)M * 2 * ((F + 63) / 64) * 8);  // per-row partial (sum, sum sq)
+  int stats_parts = 2;  // row_stats_cast_kernel writes two parts per row (the second one empty)
   void* qkv = c.ar.alloc((size_t)M * 3 * F * 2);
   void* att = c.ar.alloc((size_t)M * F * 2);
   void* hid = c.ar.alloc((size_t)M * 4 * F * 2);
@@ -672,11 +701,22 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       });
     }
   }
+  // Both LayerNorms of a block are folded into the GEMM that consumes them (weights.py: qkv.w / fc1.w carry the LN
+  // scale, *.b the LN shift, *.s the column sums): the A operand is the raw 16-bit residual stream `ln` and the row
+  // statistics `stats`, both written by the epilogue of the GEMM that last updated x (here: by one small kernel).
+  if (!c.dry) {
+    const int is_bf16 = c.is_bf16;
+    c.add("row_stats", 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
+      cudaError_t e;
+      DISPATCH_T(is_bf16, (e = launch_ex(row_stats_cast_kernel<T>, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, s, false,
+                                         (const float*)x, (T*)ln, stats, M, F)));
+      return e;
+    });
+  }
   const float scale = 1.0f / sqrtf(64.0f);
   for (int i = 0; i < L && c.ok; ++i) {
     const std::string pre = "blk" + std::to_string(i) + ".";
-    const Weight *l1w = get_w(c, pre + "ln1.w", DPT_F32), *l1b = get_w(c, pre + "ln1.b", DPT_F32);
-    const Weight *l2w = get_w(c, pre + "ln2.w", DPT_F32), *l2b = get_w(c, pre + "ln2.b", DPT_F32);
+    const Weight *qs = get_w(c, pre + "qkv.s", DPT_F32), *f1s = get_w(c, pre + "fc1.s", DPT_F32);
     const Weight *qw = get_w(c, pre + "qkv.w", hd), *qb = get_w(c, pre + "qkv.b", DPT_F32);
     const Weight *pw = get_w(c, pre + "proj.w", hd), *pb = get_w(c, pre + "proj.b", DPT_F32);
     const Weight *f1w = get_w(c, pre + "fc1.w", hd), *f1b = get_w(c, pre + "fc1.b", DPT_F32);
@@ -684,11 +724,11 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     if (!c.ok) return false;
     const int hidden = (int)f1w->shape[0];
     c.scope = pre;
-    add_layernorm(c, x, (const float*)l1w->ptr, (const float*)l1b->ptr, ln, M, F, cfg.ln_eps);
     {
-      GemmOp op;
+      GemmOp op;  // qkv = LN1(x) Wqkv^T + b
       op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = qw->ptr; op.N = 3 * F; op.kpad = (int)qw->shape[1];
       op.bias = (const float*)qb->ptr; op.out = qkv; op.label = "qkv";
+      op.ln_stats = stats; op.ln_parts = stats_parts; op.ln_colsum = (const float*)qs->ptr; op.ln_eps = cfg.ln_eps;
       add_gemm(c, op);
     }
     if (is_beit) {
@@ -714,19 +754,21 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       GemmOp op;  // x += (gamma1 . proj)(att)   (LayerScale folded into the packed weights)
       op.A = att; op.Wt = (int)M; op.C = F; op.Wt_ptr = pw->ptr; op.N = F; op.kpad = (int)pw->shape[1];
       op.bias = (const float*)pb->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x; op.label = "proj";
+      op.stats_out = stats; op.stats_parts = &stats_parts; op.out16 = ln;
       add_gemm(c, op);
     }
-    add_layernorm(c, x, (const float*)l2w->ptr, (const float*)l2b->ptr, ln, M, F, cfg.ln_eps);
     {
-      GemmOp op;
+      GemmOp op;  // hid = GELU(LN2(x) W1^T + b1)
       op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = hidden; op.kpad = (int)f1w->shape[1];
       op.bias = (const float*)f1b->ptr; op.act = ACT_GELU; op.out = hid; op.label = "fc1";
+      op.ln_stats = stats; op.ln_parts = stats_parts; op.ln_colsum = (const float*)f1s->ptr; op.ln_eps = cfg.ln_eps;
       add_gemm(c, op);
     }
     {
       GemmOp op;
       op.A = hid; op.Wt = (int)M; op.C = hidden; op.Wt_ptr = f2w->ptr; op.N = F; op.kpad = (int)f2w->shape[1];
       op.bias = (const float*)f2b->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x; op.label = "fc2";
+      op.stats_out = stats; op.stats_parts = &stats_parts; op.out16 = ln;
       add_gemm(c, op);
     }
     if ((i + 1) % per_stage == 0) {

@@ -56,6 +56,19 @@ struct __align__(64) GemmParams {
   long long ld_add2;
   void* out2_relu;    // optional second output relu(result), 16-bit, same pixel indexing
   long long ld_out2;
+  // LayerNorm folded into the consumer GEMM (pre-norm transformer blocks): A holds the RAW 16-bit residual stream and
+  // Wt = W (.) g, so  LN(x) W^T + b = rstd_m * acc - rstd_m * mean_m * colsum_n + b'_n  with the per-row statistics
+  // produced by the epilogue of the GEMM that wrote the residual stream (stats_out below).
+  const float* ln_stats;   // [rows, ln_parts, 2] partial (sum, sum of squares) of the fp32 row, or null
+  const float* ln_colsum;  // [N] sum_k Wt[n, k] of the 16-bit weights
+  int ln_parts;
+  float ln_inv_f, ln_eps;  // 1 / row length, epsilon
+  // OUT_F32 producer side: per-row partial statistics of the final fp32 values (one slot per 128-column half tile,
+  // slot = n_blk * 2 + column half; deterministic, no atomics) and a 16-bit copy of the row
+  float* stats_out;        // [rows, stats_parts, 2] or null
+  int stats_parts;
+  void* out16;             // 16-bit copy of the fp32 output (same pixel indexing), or null
+  long long ld_out16;
   float head_w[32];   // OUT_HEAD: depth = act2(relu(acc + bias) . head_w + head_b)
   float head_b;
   int head_act;       // ACT_RELU or ACT_SIGMOID
@@ -64,14 +77,18 @@ struct __align__(64) GemmParams {
 // TWO_CTA: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of
 // A and HALF of the B tile (the tensor core reads the other half from the peer's shared memory), which cuts the
 // L2 -> SM operand traffic per FLOP by a third and buys two more pipeline stages.
-template <int BLOCK_N, bool TWO_CTA = false>
+// RESPF kernels (OUT_F32 with a short K loop, see gemm_tc_kernel) carry one more per-warp buffer - the prefetched fp32
+// residual of the next 32-column unit - and pay for it with one pipeline stage.
+template <int BLOCK_N, bool TWO_CTA = false, bool F32OUT = false>
 struct GemmCfg {
-  static constexpr int STAGES = TWO_CTA ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int STAGES_BASE = TWO_CTA ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int STAGES = !F32OUT ? STAGES_BASE : (BLOCK_N == 64 ? 6 : (BLOCK_N == 32 ? 8 : STAGES_BASE - 1));
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = (TWO_CTA ? BLOCK_N / 2 : BLOCK_N) * GEMM_BLOCK_K * 2;
   static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP;
-  static constexpr int BAR_BYTES = 256 + 2 * BLOCK_N * 4;  // mbarriers + tmem ptr, bias tile [2][BLOCK_N]
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + BAR_BYTES;
+  static constexpr int RES_BYTES = F32OUT ? GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP : 0;
+  static constexpr int BAR_BYTES = 256 + 2 * BLOCK_N * 4;  // mbarriers + tmem ptr, bias tile + colsum tile [BLOCK_N] each
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + RES_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
 };
@@ -128,9 +145,12 @@ DPT_DEVICE float2 unpack2(uint32_t u, int is_bf16) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int BLOCK_N, int OUT_KIND, int ACT, bool BF16, bool TWO_CTA = false>
+// RESPF (OUT_F32 only): prefetch the fp32 residual with cp.async one unit ahead. Worth a pipeline stage when the K
+// loop is short (proj: the epilogue's global-load latency is on the critical path), not when it is long (fc2).
+template <int BLOCK_N, int OUT_KIND, int ACT, bool BF16, bool TWO_CTA = false, bool RESPF = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, TWO_CTA>;
+  static_assert(!RESPF || OUT_KIND == OUT_F32, "residual prefetch exists for fp32 outputs only");
+  using Cfg = GemmCfg<BLOCK_N, TWO_CTA, RESPF>;
   static_assert(!TWO_CTA || BLOCK_N == 256, "the 2-CTA kernel is built for BLOCK_N = 256");
   constexpr int STAGES = Cfg::STAGES;
 
@@ -140,7 +160,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
   uint8_t* staging = smem_b + STAGES * Cfg::B_BYTES;
-  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);  // [2][BLOCK_N]
+  uint8_t* resbuf = staging + Cfg::STAGING_BYTES;  // OUT_F32: per-warp prefetched residual unit
+  float* bias_s = reinterpret_cast<float*>(resbuf + Cfg::RES_BYTES);  // bias [BLOCK_N] | LN colsum [BLOCK_N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BLOCK_N);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -293,13 +314,75 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
       const long long pix = ((long long)b * p.OH + (long long)y * p.so + p.oy) * p.OW + (long long)x * p.so + p.ox;
 
-      // bias of this n-tile -> smem (zero beyond N / without bias); double-buffered by accumulator stage
-      float* bs = bias_s + as * BLOCK_N;
+      // folded LayerNorm: the partial statistics of my row; the loads are issued before the bias barriers below so
+      // that their latency overlaps (ln_parts is even: two (sum, sum sq) pairs per 16-byte load)
+      const bool has_ln = p.ln_stats != nullptr && row_ok;
+      const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + pix * (2 * p.ln_parts));
+      const int n4 = p.ln_parts >> 1;
+      float4 st4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st4[k] = (has_ln && k < n4) ? __ldg(sp + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+      // bias (and folded-LayerNorm column sums) of this n-tile -> smem, zero beyond N / when absent. Single-buffered:
+      // the first barrier waits until every epilogue warp is done with the previous tile's vectors.
+      float* bs = bias_s;
+      float* cs = bias_s + BLOCK_N;
+      named_bar_sync(1, GEMM_EPI_WARPS * 32);
       if (et < BLOCK_N) {
         const int n = n_blk * BLOCK_N + et;
-        bs[et] = (p.bias != nullptr && n < p.N && b < p.B) ? __ldg(p.bias + (long long)b * p.bias_bstride + n) : 0.0f;
+        const bool in = n < p.N && b < p.B;
+        bs[et] = (p.bias != nullptr && in) ? __ldg(p.bias + (long long)b * p.bias_bstride + n) : 0.0f;
+        cs[et] = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n) : 0.0f;
       }
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
+
+      float ln_rstd = 1.0f, ln_rm = 0.0f;
+      if (has_ln) {  // partials summed in a fixed order
+        float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sum += st4[k].x + st4[k].z;
+          sq += st4[k].y + st4[k].w;
+        }
+        for (int i = 4; i < n4; ++i) {
+          const float4 t = __ldg(sp + i);
+          sum += t.x + t.z;
+          sq += t.y + t.w;
+        }
+        const float mean = sum * p.ln_inv_f;
+        ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_f - mean * mean, 0.0f) + p.ln_eps);
+        ln_rm = -ln_rstd * mean;
+      }
+
+      // OUT_F32: rows 4*i + (lane >> 3) of this warp are the ones this lane moves in the coalesced phase. The fp32
+      // residual of a 32-column unit is fetched one unit ahead with cp.async into a per-warp buffer (unit 0: before the
+      // accumulator is even complete), which takes the global-load latency off the critical path of the short-K
+      // residual GEMMs (proj) without holding registers. Every lane reads back exactly the 16-byte slots it filled.
+      constexpr bool F32O = OUT_KIND == OUT_F32;
+      long long res_pix[F32O ? 8 : 1];
+      bool res_ok[F32O ? 8 : 1];
+      const uint32_t res_slot = smem_u32(resbuf + ew * GEMM_STAGE_BYTES_PER_WARP + lane * 16);  // + i * 512
+      auto prefetch_residual = [&](int u) {
+        if constexpr (F32O) {
+          const int col = n_blk * BLOCK_N + wg * COLS_PER_WG + u * 32 + (lane & 7) * 4;
+          if (RESPF && col < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (res_ok[i])
+                cp_async_16(res_slot + i * 512, reinterpret_cast<const float*>(p.add1) + res_pix[i] * p.ld_add1 + col);
+          }
+          cp_async_commit();
+        }
+      };
+      if constexpr (F32O) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          res_pix[i] = __shfl_sync(0xffffffffu, pix, rr);
+          res_ok[i] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0;
+        }
+        if (RESPF && wg_active && p.add1 != nullptr) prefetch_residual(0);
+      }
 
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
@@ -328,19 +411,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           constexpr int UNITS_PER_STG = NCOLS_HERE / 32;      // 1 (fp32 out) or 2 (16-bit out)
           const int sub = lane & 7;  // 16-byte chunk within a 128-byte row segment (phase 2)
           // software pipeline: the TMEM load of unit u+1 is in flight while unit u is processed / stored
-          uint32_t vbuf[2][32];
+          // (OUT_F32 keeps a prefetched residual instead of a prefetched accumulator unit: registers)
+          uint32_t vbuf[F32OUT ? 1 : 2][32];
           tmem_ld32(t_acc, vbuf[0]);
+          // OUT_F32 + stats_out: partial row statistics of rows 4*i + (lane >> 3) over this warp's column half
+          float st_sum[F32OUT ? 8 : 1], st_sq[F32OUT ? 8 : 1];
+          if constexpr (F32OUT) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              st_sum[i] = 0.0f;
+              st_sq[i] = 0.0f;
+            }
+          }
 #pragma unroll
           for (int u = 0; u < UNITS; ++u) {
-            uint32_t(&v)[32] = vbuf[u & 1];
+            uint32_t(&v)[32] = vbuf[F32OUT ? 0 : (u & 1)];
+            if constexpr (F32OUT) {
+              if (u > 0) tmem_ld32(t_acc + u * 32, vbuf[0]);
+            }
             tmem_ld_wait_dep(v);
-            if (u + 1 < UNITS) tmem_ld32(t_acc + (u + 1) * 32, vbuf[(u + 1) & 1]);
+            if constexpr (!F32OUT) {
+              if (u + 1 < UNITS) tmem_ld32(t_acc + (u + 1) * 32, vbuf[(u + 1) & 1]);
+            }
             const int c0 = (u / UNITS_PER_STG) * COLS_PER_STG;   // first column of this staging chunk
             const int cc = (u % UNITS_PER_STG) * 32;             // column offset inside the staging chunk
             // ---- phase 1: my row, 32 columns: +bias, activation -> swizzled staging
             {
               const float4* b4 = reinterpret_cast<const float4*>(bs + col_base + c0 + cc);
               float f[32];
+              if (p.ln_stats != nullptr) {
+                const float4* s4 = reinterpret_cast<const float4*>(cs + col_base + c0 + cc);
+                const float2 rs2 = make_float2(ln_rstd, ln_rstd), rm2 = make_float2(ln_rm, ln_rm);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {  // packed fp32x2 FMAs: acc * rstd + (rm * colsum + bias)
+                  const float4 bb = b4[j];
+                  const float4 ss = s4[j];
+                  const float2 t0 = __ffma2_rn(rm2, make_float2(ss.x, ss.y), make_float2(bb.x, bb.y));
+                  const float2 t1 = __ffma2_rn(rm2, make_float2(ss.z, ss.w), make_float2(bb.z, bb.w));
+                  const float2 r0 = __ffma2_rn(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), rs2, t0);
+                  const float2 r1 = __ffma2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), rs2, t1);
+                  f[4 * j + 0] = r0.x;
+                  f[4 * j + 1] = r0.y;
+                  f[4 * j + 2] = r1.x;
+                  f[4 * j + 3] = r1.y;
+                }
+              } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 bb = b4[j];
@@ -348,6 +463,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
                 f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
                 f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+              }
               }
               if constexpr (ACT == ACT_GELU) {
 #pragma unroll
@@ -388,33 +504,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const bool col_ok = (sub * ELEMS_PER_CHUNK < NCOLS_HERE) && (ncol0 + sub * ELEMS_PER_CHUNK) < p.N;
             const long long coff = ncol0 + sub * ELEMS_PER_CHUNK;
             if constexpr (F32OUT) {
-              long long rpix[8];
+              const long long(&rpix)[8] = res_pix;
               bool ok[8];
               uint4 val[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int rr = 4 * i + (lane >> 3);
-                rpix[i] = __shfl_sync(0xffffffffu, pix, rr);
-                ok[i] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
+                ok[i] = res_ok[i] && col_ok;
                 val[i] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((sub ^ (rr & 7)) * 16));
               }
               if (p.add1 != nullptr) {
-                float4 a[8];
+                if constexpr (RESPF) {
+                  cp_async_wait_all();  // this lane's own copies of this unit
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  a[i] = ok[i] ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add1) +
-                                                                  rpix[i] * p.ld_add1 + coff)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int i = 0; i < 8; ++i) {
+                    if (ok[i]) {
+                      const float4 a = lds_f4(res_slot + i * 512);
+                      float4 o = *reinterpret_cast<float4*>(&val[i]);
+                      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                      val[i] = *reinterpret_cast<uint4*>(&o);
+                    }
+                  }
+                  if (u + 1 < UNITS) prefetch_residual(u + 1);  // the slots were just read by this same lane
+                } else {
+                  float4 a[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float4 o = *reinterpret_cast<float4*>(&val[i]);
-                  o.x += a[i].x; o.y += a[i].y; o.z += a[i].z; o.w += a[i].w;
-                  val[i] = *reinterpret_cast<uint4*>(&o);
+                  for (int i = 0; i < 8; ++i)
+                    a[i] = ok[i] ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add1) +
+                                                                    rpix[i] * p.ld_add1 + coff)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float4 o = *reinterpret_cast<float4*>(&val[i]);
+                    o.x += a[i].x; o.y += a[i].y; o.z += a[i].z; o.w += a[i].w;
+                    val[i] = *reinterpret_cast<uint4*>(&o);
+                  }
                 }
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
+              if (p.stats_out != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 o = *reinterpret_cast<float4*>(&val[i]);
+                  if (ok[i]) {
+                    const float2 a = make_float2(o.x, o.y), c = make_float2(o.z, o.w);
+                    const float2 ps = __fadd2_rn(a, c);
+                    const float2 pq = __ffma2_rn(a, a, __fmul2_rn(c, c));
+                    st_sum[i] += ps.x + ps.y;
+                    st_sq[i] += pq.x + pq.y;
+                    if (p.out16 != nullptr) {
+                      uint2 h;
+                      h.x = pack2(o.x, o.y, is_bf16);
+                      h.y = pack2(o.z, o.w, is_bf16);
+                      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out16) + rpix[i] * p.ld_out16 + coff) = h;
+                    }
+                  }
+                }
+              }
             } else {
               const bool has_extra = p.add1 != nullptr || p.add2 != nullptr || p.out2_relu != nullptr;
 #pragma unroll
@@ -469,6 +617,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               }
             }
             __syncwarp();
+          }
+          if constexpr (F32OUT) {
+            if (p.stats_out != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                  st_sum[i] += __shfl_xor_sync(0xffffffffu, st_sum[i], o);
+                  st_sq[i] += __shfl_xor_sync(0xffffffffu, st_sq[i], o);
+                }
+                if (sub == 0 && res_ok[i])
+                  reinterpret_cast<float2*>(p.stats_out)[res_pix[i] * p.stats_parts + n_blk * 2 + wg] =
+                      make_float2(st_sum[i], st_sq[i]);
+              }
+            }
           }
         }
       }

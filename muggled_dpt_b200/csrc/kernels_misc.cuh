@@ -189,6 +189,35 @@ __global__ void layernorm_kernel(const TIN* __restrict__ x, const float* __restr
   }
 }
 
+// Row statistics for the LayerNorm folded into the next GEMM (gemm_tc.cuh): stats[row] = {(sum, sum of squares), (0, 0)} of the
+// fp32 row (two parts: the consumer reads pairs of parts), y = 16-bit copy of the row. One warp per row. Only the first block of an encoder needs this kernel; later
+// rows statistics come out of the epilogue of the GEMM that updates the residual stream.
+template <typename T>
+__global__ void row_stats_cast_kernel(const float* __restrict__ x, T* __restrict__ y, float* __restrict__ stats,
+                                      long long M, int F) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + row * F;
+  T* yr = y + row * F;
+  float sum = 0.0f, sq = 0.0f;
+  for (int f = lane * 4; f < F; f += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + f);
+    sum += (v.x + v.y) + (v.z + v.w);
+    sq += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+    T o[4] = {from_f32<T>(v.x), from_f32<T>(v.y), from_f32<T>(v.z), from_f32<T>(v.w)};
+    *reinterpret_cast<uint2*>(yr + f) = *reinterpret_cast<uint2*>(o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) reinterpret_cast<float4*>(stats)[row] = make_float4(sum, sq, 0.0f, 0.0f);  // two parts, second empty
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Bilinear resize, align_corners=True (misc_helpers.py:39-42), NHWC, 8 channels per thread.
 // src coordinate = dst * (in-1)/(out-1); matches ATen's area_pixel_compute_scale for align_corners.

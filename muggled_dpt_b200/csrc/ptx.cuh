@@ -120,6 +120,19 @@ DPT_DEVICE float2 ex2_poly2(float2 x) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// cp.async (16-byte global -> shared copies tracked per thread), 16-byte shared load
+DPT_DEVICE void cp_async_16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+DPT_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DPT_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+DPT_DEVICE float4 lds_f4(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // TMA
 
 DPT_DEVICE void prefetch_tmap(const CUtensorMap* m) {

@@ -200,19 +200,25 @@ class DPTModel(torch.nn.Module):
             N.check(L.dpt_create(C.byref(cfg), C.byref(handle)), None, "dpt_create")
             self._handle = handle
             self._dev_weights = {}
-            for name, (t, kind) in self._packed_cpu.items():
-                if kind == "half":
-                    d, code = t.to(device=self._device, dtype=self._dtype), _TORCH_TO_DPT[self._dtype]
-                elif kind == "f32":
-                    d, code = t.to(device=self._device, dtype=torch.float32), N.DPT_F32
-                else:  # "host": tiny fp32 vectors the library copies into the handle
-                    d, code = t.to(dtype=torch.float32).contiguous(), N.DPT_F32
+            def set_weight(name, d, code):
                 self._dev_weights[name] = d
                 shape = (C.c_int64 * max(1, d.dim()))(*d.shape)
                 N.check(
                     L.dpt_set_weight(handle, name.encode(), C.c_void_p(d.data_ptr()), shape, d.dim(), code),
                     handle, f"dpt_set_weight({name})",
                 )
+
+            for name, (t, kind) in self._packed_cpu.items():
+                if kind in ("half", "half_colsum"):
+                    d, code = t.to(device=self._device, dtype=self._dtype), _TORCH_TO_DPT[self._dtype]
+                    if kind == "half_colsum":  # LayerNorm folded into this GEMM: column sums of the ROUNDED weights
+                        assert name.endswith(".w")
+                        set_weight(name[:-2] + ".s", d.to(torch.float32).sum(dim=1).contiguous(), N.DPT_F32)
+                elif kind == "f32":
+                    d, code = t.to(device=self._device, dtype=torch.float32), N.DPT_F32
+                else:  # "host": tiny fp32 vectors the library copies into the handle
+                    d, code = t.to(dtype=torch.float32).contiguous(), N.DPT_F32
+                set_weight(name, d, code)
         self._workspace, self._ws_key, self._io = None, None, {}
 
     def _release(self):

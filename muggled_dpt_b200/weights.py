@@ -95,6 +95,18 @@ def pack_linear(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def fold_layernorm(w: torch.Tensor, b, ln_w: torch.Tensor, ln_b: torch.Tensor):
+    """Linear(LN(x)) with LN(x) = xhat * ln_w + ln_b (transformer_block.py:53-65: the norm feeds exactly one Linear):
+    W' = W * ln_w[None, :], b' = b + W @ ln_b. The GEMM then runs on the raw residual stream and its epilogue applies
+    the per-row mean / rstd (csrc/gemm_tc.cuh "folded LayerNorm"). Returns (packed W', b'); kind "half_colsum" makes
+    DPTModel.to() emit the column sums of the 16-bit W' next to it."""
+    w = w.to(torch.float32)
+    b2 = w @ ln_b.to(torch.float32)
+    if b is not None:
+        b2 = b2 + b.to(torch.float32)
+    return pack_linear(w * ln_w.to(torch.float32)[None, :]), b2
+
+
 def pack_conv(w: torch.Tensor) -> torch.Tensor:
     """Conv2d weight [Cout, Cin, kh, kw] -> [Cout, kh*kw*kpad], column = (ky*kw + kx)*kpad + ci"""
     co, ci, kh, kw = w.shape
@@ -122,7 +134,7 @@ def pack_patch_embed(w: torch.Tensor) -> torch.Tensor:
 
 
 def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
-    """Returns {packed name: (fp32 cpu tensor, kind)} with kind in {"half", "f32", "host"}."""
+    """Returns {packed name: (fp32 cpu tensor, kind)} with kind in {"half", "half_colsum", "f32", "host"}."""
     F = cfg["features_per_token"]
     L = cfg["num_blocks"]
     missing = []
@@ -152,22 +164,24 @@ def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
     put("pos.cls_tok", cls.reshape(-1) if cls is not None else None, "f32")
     for i in range(L):
         s, d = f"pretrained.blocks.{i}.", f"blk{i}."
-        put(d + "ln1.w", get(s + "norm1.weight", (F,), 1.0), "f32")
-        put(d + "ln1.b", get(s + "norm1.bias", (F,)), "f32")
-        put(d + "ln2.w", get(s + "norm2.weight", (F,), 1.0), "f32")
-        put(d + "ln2.b", get(s + "norm2.bias", (F,)), "f32")
-        qw = get(s + "attn.qkv.weight", (3 * F, F))
-        put(d + "qkv.w", pack_linear(qw) if qw is not None else None, "half")
-        put(d + "qkv.b", get(s + "attn.qkv.bias", (3 * F,)), "f32")
+        l1w, l1b = get(s + "norm1.weight", (F,), 1.0), get(s + "norm1.bias", (F,))
+        l2w, l2b = get(s + "norm2.weight", (F,), 1.0), get(s + "norm2.bias", (F,))
+        qw, qb = get(s + "attn.qkv.weight", (3 * F, F)), get(s + "attn.qkv.bias", (3 * F,))
+        if all(t is not None for t in (l1w, l1b, qw, qb)):
+            w_, b_ = fold_layernorm(qw, qb, l1w, l1b)
+            put(d + "qkv.w", w_, "half_colsum")
+            put(d + "qkv.b", b_, "f32")
         g1 = get(s + "ls1.gamma", (F,), 1.0)
         g2 = get(s + "ls2.gamma", (F,), 1.0)
         w, b = get(s + "attn.proj.weight", (F, F)), get(s + "attn.proj.bias", (F,))
         if all(t is not None for t in (g1, w, b)):
             put(d + "proj.w", pack_linear(g1[:, None] * w), "half")
             put(d + "proj.b", g1 * b, "f32")
-        w1 = get(s + "mlp.fc1.weight", (4 * F, F))
-        put(d + "fc1.w", pack_linear(w1) if w1 is not None else None, "half")
-        put(d + "fc1.b", get(s + "mlp.fc1.bias", (4 * F,)), "f32")
+        w1, b1 = get(s + "mlp.fc1.weight", (4 * F, F)), get(s + "mlp.fc1.bias", (4 * F,))
+        if all(t is not None for t in (l2w, l2b, w1, b1)):
+            w_, b_ = fold_layernorm(w1, b1, l2w, l2b)
+            put(d + "fc1.w", w_, "half_colsum")
+            put(d + "fc1.b", b_, "f32")
         w, b = get(s + "mlp.fc2.weight", (F, 4 * F)), get(s + "mlp.fc2.bias", (F,))
         if all(t is not None for t in (g2, w, b)):
             put(d + "fc2.w", pack_linear(g2[:, None] * w), "half")
@@ -285,22 +299,24 @@ def pack_beit(sd: dict, cfg: dict, strict: bool = True) -> dict:
     put("beit.cls", cls.reshape(-1) if cls is not None else None, "f32")
     for i in range(L):
         s, d = f"pretrained.model.blocks.{i}.", f"blk{i}."
-        put(d + "ln1.w", get(s + "norm1.weight"), "f32")
-        put(d + "ln1.b", get(s + "norm1.bias"), "f32")
-        put(d + "ln2.w", get(s + "norm2.weight"), "f32")
-        put(d + "ln2.b", get(s + "norm2.bias"), "f32")
-        put(d + "qkv.w", lin(s + "attn.qkv.weight"), "half")
-        qb, vb = get(s + "attn.q_bias"), get(s + "attn.v_bias")
-        if qb is not None and vb is not None:
-            put(d + "qkv.b", torch.cat([qb.reshape(-1), torch.zeros(F), vb.reshape(-1)]), "f32")
+        l1w, l1b = get(s + "norm1.weight"), get(s + "norm1.bias")
+        l2w, l2b = get(s + "norm2.weight"), get(s + "norm2.bias")
+        qw, qb, vb = get(s + "attn.qkv.weight"), get(s + "attn.q_bias"), get(s + "attn.v_bias")
+        if all(t is not None for t in (l1w, l1b, qw, qb, vb)):
+            w_, b_ = fold_layernorm(qw, torch.cat([qb.reshape(-1), torch.zeros(F), vb.reshape(-1)]), l1w, l1b)
+            put(d + "qkv.w", w_, "half_colsum")
+            put(d + "qkv.b", b_, "f32")
         put(d + "relpos.table", get(s + "attn.relative_position_bias_table"), "f32")
         g1, g2 = get(s + "gamma_1"), get(s + "gamma_2")
         w, b = get(s + "attn.proj.weight"), get(s + "attn.proj.bias")
         if all(t is not None for t in (g1, w, b)):
             put(d + "proj.w", pack_linear(g1[:, None] * w), "half")
             put(d + "proj.b", g1 * b, "f32")
-        put(d + "fc1.w", lin(s + "mlp.fc1.weight"), "half")
-        put(d + "fc1.b", get(s + "mlp.fc1.bias"), "f32")
+        w1, b1 = get(s + "mlp.fc1.weight"), get(s + "mlp.fc1.bias")
+        if all(t is not None for t in (l2w, l2b, w1, b1)):
+            w_, b_ = fold_layernorm(w1, b1, l2w, l2b)
+            put(d + "fc1.w", w_, "half_colsum")
+            put(d + "fc1.b", b_, "f32")
         w, b = get(s + "mlp.fc2.weight"), get(s + "mlp.fc2.bias")
         if all(t is not None for t in (g2, w, b)):
             put(d + "fc2.w", pack_linear(g2[:, None] * w), "half")

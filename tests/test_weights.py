@@ -139,11 +139,27 @@ def test_beit_config_and_packing():
         assert cfg[k] == v, k
     packed = Wt.pack_beit(sd, cfg)
     # q/v bias -> fused QKV bias with a zero K part (v31_beit/image_encoder_model.py:341-342)
+    # ... and LayerNorm 1 folded in: W' = W * ln_w, b' = b + W @ ln_b (weights.fold_layernorm)
     qkv_b = packed["blk2.qkv.b"][0]
     Fd = cfg["features_per_token"]
-    assert torch.equal(qkv_b[:Fd], sd["pretrained.model.blocks.2.attn.q_bias"])
-    assert torch.count_nonzero(qkv_b[Fd:2 * Fd]) == 0
-    assert torch.equal(qkv_b[2 * Fd:], sd["pretrained.model.blocks.2.attn.v_bias"])
+    Wq = sd["pretrained.model.blocks.2.attn.qkv.weight"].float()
+    ln_w, ln_b = sd["pretrained.model.blocks.2.norm1.weight"].float(), sd["pretrained.model.blocks.2.norm1.bias"].float()
+    shift = Wq @ ln_b
+    assert torch.allclose(qkv_b[:Fd], sd["pretrained.model.blocks.2.attn.q_bias"] + shift[:Fd], atol=1e-6)
+    assert torch.allclose(qkv_b[Fd:2 * Fd], shift[Fd:2 * Fd], atol=1e-6)
+    assert torch.allclose(qkv_b[2 * Fd:], sd["pretrained.model.blocks.2.attn.v_bias"] + shift[2 * Fd:], atol=1e-6)
+    assert packed["blk2.qkv.w"][1] == "half_colsum"
+    assert torch.allclose(packed["blk2.qkv.w"][0][:, :Fd], Wq * ln_w[None, :])
+    # the fold is exact in fp32: Linear(LN(x)) == rstd * (x W'^T) - rstd * mean * colsum(W') + b'
+    torch.manual_seed(1)
+    xr = torch.randn(7, Fd) * 2 + 0.3
+    ref = torch.nn.functional.layer_norm(xr, (Fd,), ln_w, ln_b, 1e-6) @ Wq.T + torch.cat(
+        [sd["pretrained.model.blocks.2.attn.q_bias"], torch.zeros(Fd), sd["pretrained.model.blocks.2.attn.v_bias"]])
+    Wp = packed["blk2.qkv.w"][0][:, :Fd]
+    mean, var = xr.mean(1, keepdim=True), xr.var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-6).rsqrt()
+    got = rstd * (xr @ Wp.T) - rstd * mean * Wp.sum(1)[None, :] + qkv_b[None, :]
+    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4)
     # readout split: W1 patch + W2 cls + b == Linear(2F,F)(cat(patch, cls))
     torch.manual_seed(0)
     patch, cls = torch.randn(5, Fd), torch.randn(1, Fd)
