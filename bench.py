@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--size", type=int, default=504)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--cpu-baseline-frames", type=int, default=3)
+    ap.add_argument("--cpu-baseline-frames", type=int, default=16, help="bounded CPU sample: frames of B=1 (about 10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
@@ -139,14 +139,21 @@ def _checkpoint_file_name(model_name):
     return f"depth_anything_v2_{model_name}_synthetic.pth"
 
 
+def host_threads():
+    """every host core this process may run on (torchrun sets OMP_NUM_THREADS=1 per rank: undo that for the CPU legs)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_cpu_oracle(model_name, size, frames, threads=None):
     """fp32 CPU restatement of the reference path (oracle/), B=1 per step: returns (frames/s, cores, sample text)"""
     import torch
 
     from oracle import dpt_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     cores = torch.get_num_threads()
     sd, fwd = _oracle_model(O, model_name)
     img = O.make_input(1, size, size, seed=2)
@@ -170,6 +177,7 @@ def run_reference(args, rank, world):
 
     from oracle import dpt_oracle as O
 
+    torch.set_num_threads(host_threads())
     cores = torch.get_num_threads()
     sd, fwd = _oracle_model(O, args.model)
     img = O.make_input(1, args.size, args.size, seed=2)
@@ -187,8 +195,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Depth-Anything-V2 {args.model} {args.size}x{args.size}, global batch {args.batch} "
-                               "(reference's effective 518 setting)", "parallelism": "host cpu"},
+        "config": {"workload": (f"MiDaS v3.1 {args.model}" if args.model.startswith(("beit", "swinv2")) else f"Depth-Anything-V2 {args.model}")
+                               + f" (synthetic seeded weights), global batch {args.batch}, 3x{args.size}x{args.size}"
+                               + (" (reference's effective 518 setting)" if args.size == 504 else "") + ", fp32 on the host CPU",
+                   "global_batch": args.batch, "parallelism": "host cpu"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

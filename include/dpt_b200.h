@@ -55,6 +55,9 @@ typedef struct dpt_config {
   int layers_per_stage[4];
   int window_h, window_w;
   int pretrained_window[4]; /* 0 = none */
+  /* Depth-Anything V1 (v1_depthanything/image_encoder_model.py:92-103): the four taps are the outputs of the LAST four
+   * blocks instead of the last block of each quarter of the encoder */
+  int taps_last4;
 } dpt_config;
 
 /* lifetime ---------------------------------------------------------------------------------------------------- */
@@ -79,6 +82,18 @@ int dpt_forward(dpt_handle h, const void* img_bchw, void* depth_bhw, void* works
  * synchronize. dev_img / dev_depth are caller-provided device staging buffers of the same sizes. */
 int dpt_forward_host(dpt_handle h, const void* host_img_bchw, void* host_depth_bhw, void* dev_img, void* dev_depth,
                      void* workspace, size_t workspace_bytes, int B, int H, int W, void* stream);
+
+/* pre / post-processing around the path ------------------------------------------ */
+/* PatchEmbed.prepare_image (v2_depthanything/patch_embed.py:103-145): uint8 BGR image [IH, IW, 3] (device) -> RGB,
+ * antialiased bilinear resize to OH x OW (F.interpolate(mode="bilinear", antialias=True, align_corners=False)),
+ * (v / 255 - mean[c]) * inv_std[c], written as 16-bit NCHW [1, 3, OH, OW]. mean / inv_std: 3 host floats (RGB order). */
+int dpt_prepare_image(const uint8_t* bgr_hwc, int IH, int IW, void* out_chw, int OH, int OW, const float* mean_rgb,
+                      const float* inv_std_rgb, int dtype, void* stream);
+/* demo_helpers/postprocess.py:22-102 in one pass pair: scale_prediction (bilinear, align_corners=False) to OH x OW,
+ * normalize_01 over the whole scaled tensor, convert_to_uint8 (truncation). depth [B, H, W] 16-bit -> out [B, OH, OW]
+ * uint8; minmax: 2 device floats of scratch (receives min, max of the scaled prediction). */
+int dpt_postprocess_u8(const void* depth_bhw, int B, int H, int W, uint8_t* out_u8, int OH, int OW, float* minmax,
+                       int dtype, void* stream);
 
 /* per-stage entry points (reference contract: simple_examples/internal_features.py:38-44) ------------------------ */
 /* PatchEmbed.forward (v2_depthanything/patch_embed.py:77-99): img -> tokens [B, gh*gw, F] 16-bit */

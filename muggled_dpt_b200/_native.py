@@ -37,6 +37,7 @@ class DptConfig(C.Structure):
         ("window_h", C.c_int),
         ("window_w", C.c_int),
         ("pretrained_window", C.c_int * 4),
+        ("taps_last4", C.c_int),
     ]
 
 
@@ -67,6 +68,8 @@ SYMBOLS = [
     ("dpt_op_attention", _I, [_VP, _VP, C.c_int64, _I, _VP, _I, _I, _I, _I, _F, _I, _VP]),
     ("dpt_op_layernorm", _I, [_VP, _VP, _VP, _VP, C.c_int64, _I, _F, _I, _VP]),
     ("dpt_op_resize_bilinear", _I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    ("dpt_prepare_image", _I, [_VP, _I, _I, _VP, _I, _I, C.POINTER(_F * 3), C.POINTER(_F * 3), _I, _VP]),
+    ("dpt_postprocess_u8", _I, [_VP, _I, _I, _I, _VP, _I, _I, _VP, _I, _VP]),
     ("dpt_op_last_error", C.c_char_p, []),
     ("dpt_last_launch_count", _I, [_VP]),
     ("dpt_profile_enable", _I, [_VP, _I]),

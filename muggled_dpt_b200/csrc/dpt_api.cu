@@ -771,8 +771,10 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       op.stats_out = stats; op.stats_parts = &stats_parts; op.out16 = ln;
       add_gemm(c, op);
     }
-    if ((i + 1) % per_stage == 0) {
-      const int st = (i + 1) / per_stage - 1;
+    // taps: last block of each quarter (DA-V2, BEiT) or the last four blocks (DA-V1, image_encoder_model.py:92-103)
+    const bool is_tap = cfg.taps_last4 ? (i >= L - 4) : ((i + 1) % per_stage == 0);
+    if (is_tap) {
+      const int st = cfg.taps_last4 ? i - (L - 4) : (i + 1) / per_stage - 1;
       c.scope = "outnorm" + std::to_string(st);
       if (!is_beit) {
         add_layernorm(c, x, (const float*)on_w->ptr, (const float*)on_b->ptr, taps[st], M, F, cfg.ln_eps);
@@ -1592,6 +1594,56 @@ int dpt_op_resize_bilinear(const void* in, void* out, int B, int IH, int IW, int
   c.is_bf16 = dtype == DPT_BF16;
   add_resize(c, in, out, B, IH, IW, OH, OW, C);
   return run_op(c, launches, stream);
+}
+
+int dpt_prepare_image(const uint8_t* bgr_hwc, int IH, int IW, void* out_chw, int OH, int OW, const float* mean_rgb,
+                      const float* inv_std_rgb, int dtype, void* stream) {
+  if (!bgr_hwc || !out_chw || !mean_rgb || !inv_std_rgb || IH <= 0 || IW <= 0 || OH <= 0 || OW <= 0 ||
+      (dtype != DPT_BF16 && dtype != DPT_F16)) {
+    g_err = "dpt_prepare_image: bad argument";
+    return DPT_ERR_INVALID;
+  }
+  const float3 mean = make_float3(mean_rgb[0], mean_rgb[1], mean_rgb[2]);
+  const float3 istd = make_float3(inv_std_rgb[0], inv_std_rgb[1], inv_std_rgb[2]);
+  const dim3 grid((unsigned)((OW + 127) / 128), (unsigned)OH);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DPT_BF16) prepare_image_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(bgr_hwc, (__nv_bfloat16*)out_chw, IH, IW, OH, OW, mean, istd);
+  else prepare_image_kernel<__half><<<grid, 128, 0, s>>>(bgr_hwc, (__half*)out_chw, IH, IW, OH, OW, mean, istd);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_err = std::string("dpt_prepare_image: ") + cudaGetErrorString(e);
+    return DPT_ERR_CUDA;
+  }
+  return DPT_OK;
+}
+
+int dpt_postprocess_u8(const void* depth_bhw, int B, int H, int W, uint8_t* out_u8, int OH, int OW, float* minmax,
+                       int dtype, void* stream) {
+  if (!depth_bhw || !out_u8 || !minmax || B <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0 ||
+      (dtype != DPT_BF16 && dtype != DPT_F16)) {
+    g_err = "dpt_postprocess_u8: bad argument";
+    return DPT_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const long long total = (long long)B * OH * OW;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)nsm * 8));
+  minmax_init_kernel<<<1, 1, 0, s>>>(minmax);
+  if (dtype == DPT_BF16) {
+    post_minmax_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)depth_bhw, minmax, B, H, W, OH, OW);
+    post_u8_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)depth_bhw, minmax, out_u8, B, H, W, OH, OW);
+  } else {
+    post_minmax_kernel<__half><<<grid, 256, 0, s>>>((const __half*)depth_bhw, minmax, B, H, W, OH, OW);
+    post_u8_kernel<__half><<<grid, 256, 0, s>>>((const __half*)depth_bhw, minmax, out_u8, B, H, W, OH, OW);
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_err = std::string("dpt_postprocess_u8: ") + cudaGetErrorString(e);
+    return DPT_ERR_CUDA;
+  }
+  return DPT_OK;
 }
 
 }  // extern "C"

@@ -374,4 +374,123 @@ __global__ void readout_vec_kernel(const T* __restrict__ tap, const float* __res
   if (lane == 0) u[warp] = acc + bias[n];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pre-processing (v2_depthanything/patch_embed.py:103-145): BGR uint8 HWC -> RGB, antialiased bilinear resize,
+// (v/255 - mean) * inv_std, NCHW 16-bit. Weights follow ATen's separable antialias kernel
+// (aten/native/cpu/UpSampleKernel.cpp, _compute_indices_min_size_weights_aa with the triangle filter):
+// scale = in/out, support = scale >= 1 ? scale : 1, center = scale * (o + 0.5), taps [xmin, xmin + xsize) with
+// xmin = max(0, int(center - support + 0.5)), xsize = min(in, int(center + support + 0.5)) - xmin,
+// w_j = tri((j + xmin - center + 0.5) / max(scale, 1)) normalised to sum 1. One thread per output pixel: the 2-D
+// weight is the product of the two 1-D weights (horizontal then vertical pass of the reference, done at once in fp32).
+__device__ __forceinline__ void aa_taps(int o, int in, int out, int& xmin, int& xsize, float& center, float& invscale,
+                                        float& total) {
+  const float scale = (float)in / (float)out;
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  center = scale * (o + 0.5f);
+  xmin = max(0, (int)(center - support + 0.5f));
+  xsize = min(in, (int)(center + support + 0.5f)) - xmin;
+  total = 0.0f;
+  for (int j = 0; j < xsize; ++j) total += fmaxf(0.0f, 1.0f - fabsf((j + xmin - center + 0.5f) * invscale));
+}
+
+template <typename T>
+__global__ void prepare_image_kernel(const uint8_t* __restrict__ bgr, T* __restrict__ out, int IH, int IW, int OH, int OW,
+                                     float3 mean, float3 inv_std) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+  if (ox >= OW) return;
+  int x0, xn, y0, yn;
+  float cx, isx, tx, cy, isy, ty;
+  aa_taps(ox, IW, OW, x0, xn, cx, isx, tx);
+  aa_taps(oy, IH, OH, y0, yn, cy, isy, ty);
+  float r = 0.0f, g = 0.0f, b = 0.0f;
+  for (int jy = 0; jy < yn; ++jy) {
+    const float wy = fmaxf(0.0f, 1.0f - fabsf((jy + y0 - cy + 0.5f) * isy)) / ty;
+    const uint8_t* row = bgr + ((size_t)(y0 + jy) * IW + x0) * 3;
+    float rr = 0.0f, gg = 0.0f, bb = 0.0f;
+    for (int jx = 0; jx < xn; ++jx) {
+      const float wx = fmaxf(0.0f, 1.0f - fabsf((jx + x0 - cx + 0.5f) * isx)) / tx;
+      bb += wx * (float)row[3 * jx + 0];
+      gg += wx * (float)row[3 * jx + 1];
+      rr += wx * (float)row[3 * jx + 2];
+    }
+    r += wy * rr;
+    g += wy * gg;
+    b += wy * bb;
+  }
+  const size_t plane = (size_t)OH * OW, o = (size_t)oy * OW + ox;
+  out[o] = from_f32<T>((r / 255.0f - mean.x) * inv_std.x);
+  out[plane + o] = from_f32<T>((g / 255.0f - mean.y) * inv_std.y);
+  out[2 * plane + o] = from_f32<T>((b / 255.0f - mean.z) * inv_std.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Post-processing (demo_helpers/postprocess.py): bilinear resize of the prediction (align_corners=False, no
+// antialias: F.interpolate default), global min / max of the SCALED tensor, then floor(255 * (v - min) / (max - min)).
+// All arithmetic in fp32 on the 16-bit prediction (the oracle is the reference's fp32 CPU arithmetic on the same values).
+template <typename T>
+__device__ __forceinline__ float scaled_prediction_at(const T* __restrict__ d, int H, int W, int OH, int OW, int oy, int ox) {
+  const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  const float fy = fmaxf(sy * (oy + 0.5f) - 0.5f, 0.0f), fx = fmaxf(sx * (ox + 0.5f) - 0.5f, 0.0f);
+  const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float v = (1.0f - ly) * ((1.0f - lx) * to_f32(d[(size_t)y0 * W + x0]) + lx * to_f32(d[(size_t)y0 * W + x1])) +
+                  ly * ((1.0f - lx) * to_f32(d[(size_t)y1 * W + x0]) + lx * to_f32(d[(size_t)y1 * W + x1]));
+  return v;
+}
+
+__global__ void minmax_init_kernel(float* mm) {
+  mm[0] = INFINITY;
+  mm[1] = -INFINITY;
+}
+
+// float atomic min / max through the ordered-integer trick (valid for any mix of signs, no NaNs expected)
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(a), __float_as_uint(v));
+}
+
+template <typename T>
+__global__ void post_minmax_kernel(const T* __restrict__ depth, float* __restrict__ mm, int B, int H, int W, int OH, int OW) {
+  const long long total = (long long)B * OH * OW;
+  float lo = INFINITY, hi = -INFINITY;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW);
+    const long long t = idx / OW;
+    const int oy = (int)(t % OH), b = (int)(t / OH);
+    const float v = scaled_prediction_at(depth + (size_t)b * H * W, H, W, OH, OW, oy, ox);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomic_min_f(mm, lo);
+    atomic_max_f(mm + 1, hi);
+  }
+}
+
+template <typename T>
+__global__ void post_u8_kernel(const T* __restrict__ depth, const float* __restrict__ mm, uint8_t* __restrict__ out, int B,
+                               int H, int W, int OH, int OW) {
+  const long long total = (long long)B * OH * OW;
+  const float lo = mm[0], range = mm[1] - mm[0];  // (data - min) / (max - min), 255.0 * x, .byte() (truncation)
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW);
+    const long long t = idx / OW;
+    const int oy = (int)(t % OH), b = (int)(t / OH);
+    const float v = scaled_prediction_at(depth + (size_t)b * H * W, H, W, OH, OW, oy, ox);
+    const float s = 255.0f * ((v - lo) / range);
+    out[idx] = (uint8_t)(int)fminf(fmaxf(s, 0.0f), 255.0f);
+  }
+}
+
 }  // namespace dpt

@@ -36,6 +36,7 @@ class _PatchEmbedStage(_Stage):
     # input normalisation constants - v2_depthanything/patch_embed.py:38-39 ; v31_beit/patch_embed.py:38-39
     NORMALISATION = {
         "depthanythingv2": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
+        "depthanythingv1": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),  # v1_depthanything/patch_embed.py:38-39
         "beit": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
         "swinv2": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),  # v31_swinv2/patch_embed.py:39-40
     }
@@ -62,14 +63,24 @@ class _PatchEmbedStage(_Stage):
         targ_hw = (largest, largest) if use_square_sizing else (img_h, img_w)
         scaled_hw = [max(1, round(side * scale / tiling)) * tiling for side in targ_hw]
         device, dtype = m._require_ready()
-        rgb = np.ascontiguousarray(image_bgr[:, :, ::-1])  # BGR -> RGB
-        chw = torch.tensor(np.transpose(rgb, (2, 0, 1)), device=device, dtype=dtype)
-        bchw = torch.nn.functional.interpolate(
-            chw.unsqueeze(0), size=scaled_hw, align_corners=False, antialias=True, mode=interpolation_mode
-        )
-        mean = torch.tensor(self.rgb_offset, device=device, dtype=dtype).view(-1, 1, 1)
-        inv_std = 1.0 / torch.tensor(self.rgb_stdev, device=device, dtype=dtype).view(-1, 1, 1)
-        return ((bchw / 255.0) - mean) * inv_std
+        if interpolation_mode != "bilinear":
+            raise NotImplementedError("prepare_image: the device kernel implements the reference's default, bilinear")
+        bgr = np.ascontiguousarray(image_bgr)
+        if bgr.dtype != np.uint8 or bgr.ndim != 3 or bgr.shape[2] != 3:
+            raise ValueError("prepare_image: expected an HxWx3 uint8 BGR image (cv2.imread format)")
+        # one kernel: BGR->RGB, antialiased bilinear resize, /255, mean / std, NCHW 16-bit (csrc prepare_image_kernel)
+        with torch.cuda.device(device):
+            raw = torch.from_numpy(bgr).to(device, non_blocking=True)
+            out = torch.empty((1, 3, scaled_hw[0], scaled_hw[1]), device=device, dtype=dtype)
+            mean = (C.c_float * 3)(*self.rgb_offset)
+            inv_std = (C.c_float * 3)(*[1.0 / v for v in self.rgb_stdev])
+            N.check(
+                N.lib().dpt_prepare_image(C.c_void_p(raw.data_ptr()), img_h, img_w, C.c_void_p(out.data_ptr()), scaled_hw[0],
+                                          scaled_hw[1], C.byref(mean), C.byref(inv_std), _TORCH_TO_DPT[dtype], m._stream()),
+                None, "dpt_prepare_image",
+            )
+            raw.record_stream(torch.cuda.current_stream(device))
+        return out
 
     def verify_input(self, image_tensor_bchw) -> bool:
         """PatchEmbed.verify_input - v2_depthanything/patch_embed.py:149-165 (+ the even-grid rule the reference only
@@ -182,6 +193,7 @@ class DPTModel(torch.nn.Module):
             cfg.patch_size_px = self.config["patch_size_px"]
             cfg.base_grid_h, cfg.base_grid_w = self.config["base_patch_grid_hw"]
             cfg.is_metric = int(bool(self.config.get("is_metric", False)))
+            cfg.taps_last4 = int(self.model_type == "depthanythingv1")
             if self.model_type == "swinv2":
                 cfg.ln_eps = 1e-5  # torch default, all SwinV2 LayerNorms
                 cfg.window_h, cfg.window_w = self.config["window_size_hw"]

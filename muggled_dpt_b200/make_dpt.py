@@ -17,6 +17,7 @@ from .weights import (
     get_model_config_from_midas_beit_state_dict,
     get_model_config_from_midas_swinv2_state_dict,
     get_model_config_from_state_dict,
+    get_model_config_from_v1_state_dict,
 )
 
 
@@ -41,10 +42,8 @@ def make_dpt_from_state_dict(
         return make_beit_dpt_from_midas_v31_state_dict(state_dict, enable_cache, enable_optimizations, strict_load)
     if model_type == "swinv2":
         return make_swinv2_dpt_from_midas_v31_state_dict(state_dict, enable_cache, enable_optimizations, strict_load)
-    if model_type != "depthanythingv2":
-        raise NotImplementedError(
-            f"Model type {model_type} is recognised but its B200 encoder is not built yet (SURVEY.md section 8f)"
-        )
+    if model_type == "depthanythingv1":
+        return make_depthanythingv1_dpt_from_original_state_dict(state_dict, enable_cache, enable_optimizations, strict_load)
 
     # metric models are indistinguishable by weights; the reference keys off the file name (make_dpt.py:56-66)
     if model_type == "depthanythingv2" and "metric" in path_to_state_dict:
@@ -69,6 +68,22 @@ def make_depthanythingv2_dpt_from_original_state_dict(
               "  Some weights may be missing or unused!", sep="\n", flush=True)
     config_dict = get_model_config_from_state_dict(state_dict, enable_cache, enable_optimizations)
     model = DPTModel(config_dict, state_dict, strict_load=strict_load)
+    return config_dict, model
+
+
+def make_depthanythingv1_dpt_from_original_state_dict(
+    state_dict: dict,
+    enable_cache: bool = False,
+    enable_optimizations: bool = True,
+    strict_load: bool = True,
+) -> tuple[dict, DPTModel]:
+    """make_depthanythingv1_dpt.py:24-61. Same weights schema and kernels as V2; the encoder taps are the outputs of
+    the last four blocks (v1_depthanything/image_encoder_model.py:92-103) and there is no metric / giant variant."""
+    if not strict_load:
+        print("", "WARNING:", "  Loading model weights without 'strict' mode enabled!",
+              "  Some weights may be missing or unused!", sep="\n", flush=True)
+    config_dict = get_model_config_from_v1_state_dict(state_dict, enable_cache, enable_optimizations)
+    model = DPTModel(config_dict, state_dict, strict_load=strict_load, model_type="depthanythingv1")
     return config_dict, model
 
 

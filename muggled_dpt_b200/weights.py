@@ -79,6 +79,15 @@ def get_model_config_from_state_dict(state_dict: dict, enable_cache: bool, enabl
     }
 
 
+def get_model_config_from_v1_state_dict(state_dict: dict, enable_cache: bool, enable_optimizations: bool) -> dict:
+    """v1_depthanything/state_dict_conversion/config_from_original_state_dict.py:17-37: the V2 inference without the
+    is_giant / is_metric keys (same weight schema, same key order otherwise)"""
+    cfg = get_model_config_from_state_dict(state_dict, enable_cache, enable_optimizations)
+    cfg.pop("is_giant")
+    cfg.pop("is_metric")
+    return cfg
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # packing helpers (pure tensor reshapes - unit-tested on CPU in tests/test_weights.py)
 

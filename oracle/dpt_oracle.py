@@ -111,10 +111,11 @@ def encoder(sd: dict, cfg: dict, tokens: torch.Tensor, grid_hw, use_sdpa: bool =
     cls = (sd["pretrained.cls_token"] + cls_pos).to(tokens.dtype)
     x = torch.cat((cls.expand(tokens.shape[0], -1, -1), tokens + patch_pos.to(tokens.dtype)), dim=1)
     per_stage = int(round(cfg["num_blocks"] / 4))
+    last4 = bool(cfg.get("taps_last4", False))  # Depth-Anything V1: v1_depthanything/image_encoder_model.py:92-103
     taps = []
     for i in range(cfg["num_blocks"]):
         x = block(sd, i, x, cfg["num_heads"], use_sdpa)
-        if (i + 1) % per_stage == 0:
+        if (i >= cfg["num_blocks"] - 4) if last4 else ((i + 1) % per_stage == 0):
             taps.append(x)
     nw, nb = sd["pretrained.norm.weight"], sd["pretrained.norm.bias"]
     return tuple(layernorm(t, nw, nb) for t in taps[:4])
@@ -190,6 +191,47 @@ def forward(sd: dict, img_bchw: torch.Tensor, cfg: dict | None = None, return_st
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# pre / post-processing around the path
+
+NORMALISATION = {  # v2_depthanything/patch_embed.py:38-39 ; v31_beit/patch_embed.py:38-39 ; v31_swinv2/patch_embed.py:39-40
+    "depthanythingv2": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
+    "depthanythingv1": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
+    "beit": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+    "swinv2": ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+}
+
+
+def prepare_image(image_bgr, patch: int, base_grid: int, model_type: str = "depthanythingv2", max_side_length=None,
+                  use_square_sizing: bool = True) -> torch.Tensor:
+    """PatchEmbed.prepare_image - v2_depthanything/patch_embed.py:103-145, fp32 CPU (image_bgr: HxWx3 uint8 ndarray)"""
+    import numpy as np
+
+    tiling = round((8 if model_type == "swinv2" else 2) * patch)
+    if max_side_length is None:
+        max_side_length = base_grid * patch
+    img_h, img_w = image_bgr.shape[0:2]
+    largest = max(img_h, img_w)
+    scale = max_side_length / largest
+    targ_hw = (largest, largest) if use_square_sizing else (img_h, img_w)
+    scaled_hw = [max(1, round(side * scale / tiling)) * tiling for side in targ_hw]
+    rgb = np.ascontiguousarray(image_bgr[:, :, ::-1])
+    chw = torch.tensor(np.transpose(rgb, (2, 0, 1)), dtype=torch.float32)
+    bchw = F.interpolate(chw.unsqueeze(0), size=scaled_hw, align_corners=False, antialias=True, mode="bilinear")
+    mean, std = NORMALISATION[model_type]
+    mean = torch.tensor(mean).view(-1, 1, 1)
+    inv_std = 1.0 / torch.tensor(std).view(-1, 1, 1)
+    return ((bchw / 255.0) - mean) * inv_std
+
+
+def postprocess_u8(prediction_bhw: torch.Tensor, target_wh) -> torch.Tensor:
+    """convert_to_uint8(scale_prediction(prediction, target_wh)) - demo_helpers/postprocess.py:22-31,75-102"""
+    target_hw = (int(target_wh[1]), int(target_wh[0]))
+    scaled = F.interpolate(prediction_bhw.unsqueeze(1), size=target_hw, mode="bilinear").squeeze(1)
+    lo, hi = scaled.min(), scaled.max()
+    return (255.0 * ((scaled - lo) / (hi - lo))).byte()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # synthetic upstream-format checkpoints (SURVEY.md section 8c: key schema + weight distributions that give O(1) stages)
 
 STANDARD_CONFIGS = {
@@ -199,6 +241,8 @@ STANDARD_CONFIGS = {
     "vitl": dict(F=1024, blocks=24, reasm=(256, 512, 1024, 1024), C=256),
     # not a real model: small enough to commit its weights-free fixtures and run anywhere in milliseconds
     "tiny": dict(F=128, blocks=4, reasm=(16, 32, 64, 128), C=32),
+    # 8 blocks: the V1 tap rule (last four blocks) and the V2 rule (every second block) differ
+    "tiny8": dict(F=128, blocks=8, reasm=(16, 32, 64, 128), C=32),
 }
 
 

@@ -1,0 +1,70 @@
+"""CPU: the rows added after the core path - the oracle restatements of the Depth-Anything V1 tap
+rule, the metric head, PatchEmbed.prepare_image and the demo post-processing chain against golden vectors produced by
+the real reference (oracle/make_golden_widen.py), plus the host logic (type sniffing, V1 config keys)."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+from oracle import dpt_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_oracle_v1_taps_match_reference_every_stage():
+    fix = torch.load(os.path.join(GOLDEN, "da_v1_tiny8.pt"))
+    sd = O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"])
+    cfg = O.infer_config(sd)
+    cfg["taps_last4"] = True
+    st = O.forward(sd, fix["img"], cfg=cfg, return_stages=True)
+    for a, b in zip(st["taps"], fix["taps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=2e-5)
+    torch.testing.assert_close(st["depth"], fix["depth"], rtol=0, atol=1e-4)
+    # the V2 rule on the same weights gives different taps: the fixture discriminates the two rules
+    st2 = O.forward(sd, fix["img"], return_stages=True)
+    assert (st2["taps"][0] - fix["taps"][0]).abs().max() > 1e-2
+
+
+def test_oracle_metric_head_matches_reference():
+    fix = torch.load(os.path.join(GOLDEN, "da_v2_metric.pt"))
+    sd = O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"])
+    sd["is_metric"] = torch.tensor(1.0)
+    depth = O.forward(sd, fix["img"])
+    torch.testing.assert_close(depth, fix["depth"], rtol=0, atol=1e-5)
+    assert 0.0 < depth.min() and depth.max() < 1.0  # Sigmoid range
+
+
+def test_oracle_prepare_image_matches_reference():
+    for case in torch.load(os.path.join(GOLDEN, "prepare_image.pt")):
+        out = O.prepare_image(case["bgr"].numpy(), case["patch"], case["base_grid"], case["model_type"], **case["kwargs"])
+        assert out.shape == case["out"].shape, case["name"]
+        torch.testing.assert_close(out, case["out"], rtol=0, atol=1e-6)
+
+
+def test_oracle_postprocess_matches_reference():
+    for case in torch.load(os.path.join(GOLDEN, "postprocess.pt")):
+        out = O.postprocess_u8(case["pred"].float(), case["target_wh"])
+        assert out.dtype == torch.uint8 and torch.equal(out, case["out"])
+
+
+def test_v1_factory_type_sniffing_and_config_keys():
+    from muggled_dpt_b200 import make_dpt_from_state_dict
+    from muggled_dpt_b200.weights import determine_model_type_from_state_dict
+
+    fix = torch.load(os.path.join(GOLDEN, "da_v1_tiny8.pt"))
+    sd = O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"])
+    # make_dpt.py:98-104: the version comes from the FILE NAME
+    assert determine_model_type_from_state_dict("/x/depth_anything_vitl14.pth", sd) == "depthanythingv1"
+    assert determine_model_type_from_state_dict("/x/depth_anything_v1_vits.pth", sd) == "depthanythingv1"
+    assert determine_model_type_from_state_dict("/x/depth_anything_v2_vits.pth", sd) == "depthanythingv2"
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "depth_anything_v1_synthetic.pth")
+        torch.save(sd, path)
+        cfg, model = make_dpt_from_state_dict(path)
+    assert model.model_type == "depthanythingv1"
+    assert list(cfg.keys()) == list(fix["config"].keys())  # no is_giant / is_metric keys in the V1 config
+    for k, v in fix["config"].items():
+        assert (list(cfg[k]) if isinstance(cfg[k], (list, tuple)) else cfg[k]) == v, k
+    with pytest.raises(RuntimeError):
+        model.to("cpu")  # CUDA-only, like every other variant
