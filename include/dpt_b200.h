@@ -58,6 +58,9 @@ typedef struct dpt_config {
   /* Depth-Anything V1 (v1_depthanything/image_encoder_model.py:92-103): the four taps are the outputs of the LAST four
    * blocks instead of the last block of each quarter of the encoder */
   int taps_last4;
+  /* ViT-G (v2_depthanything/components/misc_helpers.py:125-185): the block MLP is the SwiGLU FFN - fc1 holds the doubled
+   * inner Linear [2h, F] (gate half first), fc2 the outer Linear [F, h] */
+  int mlp_swiglu;
 } dpt_config;
 
 /* lifetime ---------------------------------------------------------------------------------------------------- */

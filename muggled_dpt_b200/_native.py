@@ -38,6 +38,7 @@ class DptConfig(C.Structure):
         ("window_w", C.c_int),
         ("pretrained_window", C.c_int * 4),
         ("taps_last4", C.c_int),
+        ("mlp_swiglu", C.c_int),
     ]
 
 

@@ -660,6 +660,12 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
   void* qkv = c.ar.alloc((size_t)M * 3 * F * 2);
   void* att = c.ar.alloc((size_t)M * F * 2);
   void* hid = c.ar.alloc((size_t)M * 4 * F * 2);
+  void* inner = nullptr;  // ViT-G: output of the doubled inner Linear of the SwiGLU FFN [M, 2h]
+  if (cfg.mlp_swiglu) {
+    const Weight* w0 = get_w(c, "blk0.fc1.w", hd);
+    if (!w0) return false;
+    inner = c.ar.alloc((size_t)M * (size_t)w0->shape[0] * 2);
+  }
 
   const bool is_beit = cfg.variant == DPT_VARIANT_BEIT;
   const Weight *on_w = nullptr, *on_b = nullptr;
@@ -722,7 +728,10 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     const Weight *f1w = get_w(c, pre + "fc1.w", hd), *f1b = get_w(c, pre + "fc1.b", DPT_F32);
     const Weight *f2w = get_w(c, pre + "fc2.w", hd), *f2b = get_w(c, pre + "fc2.b", DPT_F32);
     if (!c.ok) return false;
-    const int hidden = (int)f1w->shape[0];
+    // ViT-G: fc1 is the doubled inner Linear of the SwiGLU FFN [2h, F], fc2 the outer Linear [F, h] (K padded to 64)
+    const bool swiglu = cfg.mlp_swiglu != 0;
+    const int hidden = swiglu ? (int)f1w->shape[0] / 2 : (int)f1w->shape[0];
+    if (swiglu && hidden % 8 != 0) return c.fail("SwiGLU: the hidden width must be a multiple of 8");
     c.scope = pre;
     {
       GemmOp op;  // qkv = LN1(x) Wqkv^T + b
@@ -759,14 +768,28 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     }
     {
       GemmOp op;  // hid = GELU(LN2(x) W1^T + b1)
-      op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = hidden; op.kpad = (int)f1w->shape[1];
-      op.bias = (const float*)f1b->ptr; op.act = ACT_GELU; op.out = hid; op.label = "fc1";
+      op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = swiglu ? 2 * hidden : hidden;
+      op.kpad = (int)f1w->shape[1];
+      op.bias = (const float*)f1b->ptr; op.act = swiglu ? ACT_NONE : ACT_GELU; op.out = swiglu ? inner : hid; op.label = "fc1";
       op.ln_stats = stats; op.ln_parts = stats_parts; op.ln_colsum = (const float*)f1s->ptr; op.ln_eps = cfg.ln_eps;
       add_gemm(c, op);
     }
+    const int hidden_pad = (int)f2w->shape[1];  // fc2's K, a multiple of 64
+    if (swiglu && !c.dry) {
+      // gate: hid[m, j] = silu(inner[m, j]) * inner[m, h + j]
+      if (hidden_pad > 4 * F) return c.fail("SwiGLU: hidden width exceeds the block buffers");
+      const int is_bf16 = c.is_bf16, nsm = c.num_sms;
+      c.add("swiglu:" + pre, 0.0, (double)M * 3.0 * hidden * 2.0, [=](cudaStream_t s) {
+        const int grid = ew_grid(M * (hidden_pad / 8), 256, nsm);
+        cudaError_t e;
+        DISPATCH_T(is_bf16, (e = launch_ex(swiglu_kernel<T>, dim3(grid), dim3(256), 0, s, false, (const T*)inner, (T*)hid, M,
+                                           hidden, hidden_pad)));
+        return e;
+      });
+    }
     {
       GemmOp op;
-      op.A = hid; op.Wt = (int)M; op.C = hidden; op.Wt_ptr = f2w->ptr; op.N = F; op.kpad = (int)f2w->shape[1];
+      op.A = hid; op.Wt = (int)M; op.C = swiglu ? hidden_pad : hidden; op.Wt_ptr = f2w->ptr; op.N = F; op.kpad = hidden_pad;
       op.bias = (const float*)f2b->ptr; op.out_kind = OUT_F32; op.out = x; op.add1 = x; op.label = "fc2";
       op.stats_out = stats; op.stats_parts = &stats_parts; op.out16 = ln;
       add_gemm(c, op);

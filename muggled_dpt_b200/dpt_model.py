@@ -102,8 +102,6 @@ class DPTModel(torch.nn.Module):
         super().__init__()
         self.config = dict(config)
         self.model_type = model_type
-        if self.config.get("is_giant", False):
-            raise NotImplementedError("ViT-G (SwiGLU) is not built in this round")
         if model_type == "swinv2":
             fs, hs = self.config["features_per_stage"], self.config["heads_per_stage"]
             if any(f != 32 * h for f, h in zip(fs, hs)) or any(b != a * 2 for a, b in zip(fs, fs[1:])):
@@ -194,6 +192,7 @@ class DPTModel(torch.nn.Module):
             cfg.base_grid_h, cfg.base_grid_w = self.config["base_patch_grid_hw"]
             cfg.is_metric = int(bool(self.config.get("is_metric", False)))
             cfg.taps_last4 = int(self.model_type == "depthanythingv1")
+            cfg.mlp_swiglu = int(bool(self.config.get("is_giant", False)))
             if self.model_type == "swinv2":
                 cfg.ln_eps = 1e-5  # torch default, all SwinV2 LayerNorms
                 cfg.window_h, cfg.window_w = self.config["window_size_hw"]

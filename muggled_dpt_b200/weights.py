@@ -186,12 +186,18 @@ def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
         if all(t is not None for t in (g1, w, b)):
             put(d + "proj.w", pack_linear(g1[:, None] * w), "half")
             put(d + "proj.b", g1 * b, "f32")
-        w1, b1 = get(s + "mlp.fc1.weight", (4 * F, F)), get(s + "mlp.fc1.bias", (4 * F,))
+        if cfg.get("is_giant", False):
+            # ViT-G: SwiGLU FFN (components/misc_helpers.py:125-185) - w12 is the doubled inner Linear (gate half first),
+            # w3 the outer Linear; they take the places of fc1 / fc2 (dpt_config.mlp_swiglu)
+            w1, b1 = get(s + "mlp.w12.weight"), get(s + "mlp.w12.bias")
+            w, b = get(s + "mlp.w3.weight"), get(s + "mlp.w3.bias")
+        else:
+            w1, b1 = get(s + "mlp.fc1.weight", (4 * F, F)), get(s + "mlp.fc1.bias", (4 * F,))
+            w, b = get(s + "mlp.fc2.weight", (F, 4 * F)), get(s + "mlp.fc2.bias", (F,))
         if all(t is not None for t in (l2w, l2b, w1, b1)):
             w_, b_ = fold_layernorm(w1, b1, l2w, l2b)
             put(d + "fc1.w", w_, "half_colsum")
             put(d + "fc1.b", b_, "f32")
-        w, b = get(s + "mlp.fc2.weight", (F, 4 * F)), get(s + "mlp.fc2.bias", (F,))
         if all(t is not None for t in (g2, w, b)):
             put(d + "fc2.w", pack_linear(g2[:, None] * w), "half")
             put(d + "fc2.b", g2 * b, "f32")

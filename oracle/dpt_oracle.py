@@ -91,7 +91,12 @@ def attention(sd: dict, pre: str, x: torch.Tensor, heads: int, use_sdpa: bool = 
 
 
 def mlp(sd: dict, pre: str, x: torch.Tensor):
-    """MLP2Layers.forward - components/misc_helpers.py:88-120 (exact-erf GELU)"""
+    """MLP2Layers.forward - components/misc_helpers.py:88-120 (exact-erf GELU); ViT-G checkpoints carry the SwiGLU FFN
+    instead (SwiGLU.forward - components/misc_helpers.py:169-185: silu(first half) * second half of one doubled Linear)"""
+    if pre + "mlp.w12.weight" in sd:
+        inner = F.linear(x, sd[pre + "mlp.w12.weight"], sd[pre + "mlp.w12.bias"])
+        gate, lin = inner.chunk(2, dim=-1)
+        return F.linear(F.silu(gate) * lin, sd[pre + "mlp.w3.weight"], sd[pre + "mlp.w3.bias"])
     h = F.gelu(F.linear(x, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))
     return F.linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
 
@@ -309,6 +314,29 @@ def make_synthetic_state_dict(name: str = "vits", seed: int = 0, base_grid: int 
     sd["depth_head.scratch.output_conv2.2.weight"] = fan(1, 32, 1, 1)
     sd["depth_head.scratch.output_conv2.2.bias"] = torch.full((1,), 2.0)
     return sd
+
+
+def swiglu_hidden_features(features: int, ratio: float = 4) -> int:
+    """SwiGLU.__init__ - components/misc_helpers.py:161-163"""
+    return 8 * ((int(int(ratio * features) * 2 / 3) + 7) // 8)
+
+
+def giantify(sd: dict, seed: int = 0) -> dict:
+    """Turns a synthetic Depth-Anything checkpoint into the ViT-G schema: every block's fc1 / fc2 pair is replaced by
+    the SwiGLU FFN tensors mlp.w12 [2h, F] / mlp.w3 [F, h] (config_from_original_state_dict.py:248-259 keys off
+    pretrained.blocks.0.mlp.w12.weight). Separate RNG stream: the base checkpoint's tensors keep their values."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    out = {k: v for k, v in sd.items() if ".mlp.fc" not in k}
+    feats = int(sd["pretrained.patch_embed.proj.weight"].shape[0])
+    h = swiglu_hidden_features(feats)
+    blocks = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("pretrained.blocks."))
+    for i in range(blocks):
+        p = f"pretrained.blocks.{i}.mlp."
+        out[p + "w12.weight"] = torch.randn(2 * h, feats, generator=g) * feats**-0.5 * 1.5
+        out[p + "w12.bias"] = torch.randn(2 * h, generator=g) * 0.1
+        out[p + "w3.weight"] = torch.randn(feats, h, generator=g) * h**-0.5
+        out[p + "w3.bias"] = torch.randn(feats, generator=g) * 0.1
+    return out
 
 
 def make_input(B: int, H: int, W: int, seed: int = 0) -> torch.Tensor:

@@ -5,6 +5,7 @@ imported from /root/reference (build container only). Run:  python oracle/make_g
 
   da_v1_tiny8.pt  - Depth-Anything V1 tap rule: an 8-block synthetic checkpoint loaded through the reference's own
                     factory under a "v1" file name (make_dpt.py:98-104), every stage tensor
+  da_v2_giant_tiny.pt - the ViT-G block structure (SwiGLU FFN, detected from the mlp.w12 keys), taps + depth
   da_v2_metric.pt - the metric head (Sigmoid) through the "metric" file-name switch (make_dpt.py:56-66), depth only
   prepare_image.pt - PatchEmbed.prepare_image of the reference on seeded uint8 BGR images (three sizes / models)
   postprocess.pt  - demo_helpers/postprocess.py scale_prediction + convert_to_uint8 on seeded predictions
@@ -69,6 +70,21 @@ def main():
                 "sd_name": "tiny", "sd_base_grid": 5, "sd_checksum": state_dict_checksum(sd), "img": img, "depth": depth},
                os.path.join(out_dir, "da_v2_metric.pt"))
     print("da_v2_metric: depth range", depth.min().item(), depth.max().item(), "is_metric", cfg.get("is_metric"))
+
+    # ---- ViT-G structure (SwiGLU FFN): detected from the mlp.w12 keys
+    sd = O.giantify(O.make_synthetic_state_dict("tiny", seed=6, base_grid=5), seed=6)
+    img = O.make_input(2, 84, 56, seed=4)
+    cfg, model = load_reference(sd, "depth_anything_v2_vitg_synthetic.pth")
+    assert cfg["is_giant"] is True
+    with torch.inference_mode():
+        tokens, grid_hw = model.patch_embed(img)
+        taps = model.imgencoder(tokens, grid_hw)
+        depth = model(img)
+    torch.save({"config": {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in cfg.items()}, "sd_seed": 6,
+                "sd_name": "tiny", "sd_base_grid": 5, "sd_checksum": state_dict_checksum(sd), "img": img,
+                "tokens": tokens, "taps": list(taps), "depth": depth, "grid_hw": tuple(grid_hw)},
+               os.path.join(out_dir, "da_v2_giant_tiny.pt"))
+    print("da_v2_giant_tiny: depth std", depth.std().item(), "taps std", [round(t.std().item(), 3) for t in taps])
 
     # ---- prepare_image: the reference's own patch-embed modules
     from muggled_dpt.v2_depthanything.patch_embed import PatchEmbed as PE2

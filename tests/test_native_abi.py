@@ -35,5 +35,5 @@ def test_version_and_error_strings_without_gpu():
 def test_config_struct_layout_matches_header():
     from muggled_dpt_b200 import _native as N
 
-    # 14 ints + 1 float + 14 ints (SwinV2 block) + taps_last4, no padding
-    assert ctypes.sizeof(N.DptConfig) == 30 * 4
+    # 14 ints + 1 float + 14 ints (SwinV2 block) + taps_last4 + mlp_swiglu, no padding
+    assert ctypes.sizeof(N.DptConfig) == 31 * 4

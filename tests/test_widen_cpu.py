@@ -68,3 +68,29 @@ def test_v1_factory_type_sniffing_and_config_keys():
         assert (list(cfg[k]) if isinstance(cfg[k], (list, tuple)) else cfg[k]) == v, k
     with pytest.raises(RuntimeError):
         model.to("cpu")  # CUDA-only, like every other variant
+
+
+def test_oracle_vit_giant_swiglu_matches_reference():
+    fix = torch.load(os.path.join(GOLDEN, "da_v2_giant_tiny.pt"))
+    sd = O.giantify(O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"]), seed=fix["sd_seed"])
+    from oracle.make_golden import state_dict_checksum
+
+    assert state_dict_checksum(sd) == fix["sd_checksum"]
+    st = O.forward(sd, fix["img"], return_stages=True)
+    for a, b in zip(st["taps"], fix["taps"]):
+        torch.testing.assert_close(a, b, rtol=0, atol=2e-5)
+    torch.testing.assert_close(st["depth"], fix["depth"], rtol=0, atol=1e-4)
+
+
+def test_vit_giant_config_and_packing():
+    from muggled_dpt_b200 import weights as Wt
+
+    fix = torch.load(os.path.join(GOLDEN, "da_v2_giant_tiny.pt"))
+    sd = O.giantify(O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"]), seed=fix["sd_seed"])
+    cfg = Wt.get_model_config_from_state_dict(sd, False, True)
+    assert cfg["is_giant"] is True and list(cfg.keys()) == list(fix["config"].keys())
+    packed = Wt.pack_depthanything_v2(sd, cfg)
+    Fd, h = cfg["features_per_token"], O.swiglu_hidden_features(cfg["features_per_token"])
+    assert packed["blk1.fc1.w"][0].shape == (2 * h, Fd) and packed["blk1.fc1.w"][1] == "half_colsum"
+    assert packed["blk1.fc2.w"][0].shape == (Fd, (h + 63) // 64 * 64)  # K padded to the GEMM chunk with zeros
+    assert torch.count_nonzero(packed["blk1.fc2.w"][0][:, h:]) == 0

@@ -115,3 +115,24 @@ def test_postprocess_kernels_against_reference_golden():
         assert out.min().item() == 0 and out.max().item() == 255
     with pytest.raises(RuntimeError):
         scale_normalize_to_uint8(torch.zeros(1, 4, 4, dtype=torch.bfloat16), (8, 8))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_vit_giant_swiglu_against_reference_golden(dtype):
+    from oracle import dpt_oracle as O
+
+    fix = torch.load(os.path.join(GOLDEN, "da_v2_giant_tiny.pt"))
+    sd = O.giantify(O.make_synthetic_state_dict(fix["sd_name"], fix["sd_seed"], fix["sd_base_grid"]), seed=fix["sd_seed"])
+    cfg, model = _load(sd, dtype, "depth_anything_v2_vitg_synthetic.pth")
+    assert cfg["is_giant"] is True
+    img = fix["img"].to("cuda", dtype)
+    with torch.inference_mode():
+        taps = model.imgencoder(fix["tokens"].to("cuda", dtype), tuple(fix["grid_hw"]))
+        depth = model(img)
+    for k, (a, b) in enumerate(zip(taps, fix["taps"])):
+        e = _rel_l2(a, b)
+        print(f"giant tap{k} {dtype} rel_l2 {e:.2e}")
+        assert e < REL_L2[dtype], (k, e)
+    e = _rel_l2(depth, fix["depth"])
+    print(f"giant depth {dtype} rel_l2 {e:.2e}")
+    assert e < 2 * REL_L2[dtype], e

@@ -45,5 +45,11 @@ if [ -z "$SKIP_NCU" ]; then
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --profile-steps 0 > $OUT/ncu_gemm.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"layernorm|resize|row_stats" --launch-skip 30 -c 10 -f -o $OUT/ncu_misc \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --profile-steps 0 > $OUT/ncu_misc.log 2>&1
+  # keep the box output small (gpurun merges <= 64 MiB back): export the pages that get read, drop the reports
+  for r in attn gemm misc; do
+    ncu -i $OUT/ncu_$r.ncu-rep --page raw --csv > $OUT/ncu_${r}_raw.csv 2>/dev/null
+  done
+  ncu -i $OUT/ncu_attn.ncu-rep --page source --csv > $OUT/ncu_attn_source.csv 2>/dev/null
+  rm -f $OUT/ncu_gemm.ncu-rep $OUT/ncu_misc.ncu-rep
 fi
 ls -la $OUT
