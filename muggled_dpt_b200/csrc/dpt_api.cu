@@ -15,6 +15,7 @@
 
 #include "dpt_b200.h"
 #include "attn_tc.cuh"
+#include "conv_halo.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_misc.cuh"
 #include "kernels_swin.cuh"
@@ -442,6 +443,67 @@ bool add_gemm(Ctx& c, GemmOp op) {
     c.add(std::string(two_cta ? "gemm256x2" : "gemm" + std::to_string(bn)) + ":" + c.scope + op.label, flops, bytes,
           [p, bn, grid, two_cta](cudaStream_t s) { return launch_gemm(p, bn, grid, two_cta, s); });
   }
+  return true;
+}
+
+// Depth-head convolution (3x3 -> 32 channels -> ReLU -> 1x1 -> act) with the halo-tile kernel (conv_halo.cuh).
+// DPT_HALO=0 falls back to the generic nine-load spatial GEMM (A/B switch for tools/, same results).
+bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_HALO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <bool BF16>
+cudaError_t launch_halo_inst(const HaloParams& p, int grid, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_head_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HALO_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_ex(conv3x3_halo_head_kernel<BF16>, dim3((unsigned)grid), dim3(HALO_THREADS), HALO_SMEM_BYTES, s, false, p);
+}
+
+// in [B, H, W, C] 16-bit (C <= 128), Wt [32, 9 * kpad], out [B, H, W]
+bool add_conv_halo_head(Ctx& c, const void* in, const void* Wt, int kpad, const float* bias, const float* head_w,
+                        float head_b, int head_act, void* out, int B, int H, int W, int C, const char* label) {
+  if (c.dry) return true;
+  HaloParams p;
+  memset(&p, 0, sizeof p);
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H};
+    uint32_t box[4] = {64, HALO_PW, HALO_PH, 1};
+    if (!make_tmap(&p.tmA, in, 4, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * kpad, (uint64_t)HALO_N};
+    uint64_t str[1] = {(uint64_t)9 * kpad * 2};
+    uint32_t box[2] = {64, HALO_N};
+    if (!make_tmap(&p.tmB, Wt, 2, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
+  }
+  p.W = W; p.H = H; p.B = B;
+  p.tiles_x = (W + HALO_TW - 1) / HALO_TW;
+  p.tiles_y = (H + HALO_TH - 1) / HALO_TH;
+  p.kchunks = kpad / 64;
+  p.is_bf16 = c.is_bf16;
+  p.bias = bias;
+  memcpy(p.head_w, head_w, 32 * sizeof(float));
+  p.head_b = head_b;
+  p.head_act = head_act;
+  p.out = out;
+  const long long total = (long long)B * p.tiles_x * p.tiles_y;
+  const int grid = (int)std::min<long long>(total, c.num_sms);
+  const double pix = (double)B * H * W;
+  const int is_bf16 = c.is_bf16;
+  c.add(std::string("conv_halo32:") + c.scope + label, 2.0 * pix * HALO_N * C * 9,
+        pix * C * 2.0 + 9.0 * kpad * HALO_N * 2.0 + pix * 2.0,
+        [p, grid, is_bf16](cudaStream_t s) { return is_bf16 ? launch_halo_inst<true>(p, grid, s) : launch_halo_inst<false>(p, grid, s); });
   return true;
 }
 
@@ -1268,7 +1330,12 @@ bool build_head(Ctx& c, const void* fused, void* depth, int B, int h, int w) {
     add_gemm(c, op);
   }
   add_resize(c, h1, h2, B, h, w, OH, OW, C2);
-  {
+  const int kpad2 = (int)w2->shape[1] / 9;
+  if (halo_enabled() && (int)w2->shape[0] == HALO_N && kpad2 <= 64 * HALO_MAX_KCHUNKS && C2 % 8 == 0) {
+    c.scope = "head.";
+    add_conv_halo_head(c, h2, w2->ptr, kpad2, (const float*)b2->ptr, (const float*)w3->ptr, *(const float*)b3->ptr,
+                       cfg.is_metric ? ACT_SIGMOID : ACT_RELU, depth, B, OH, OW, C2, "c2c3");
+  } else {
     GemmOp op;
     op.A = h2; op.B = B; op.Ht = OH; op.Wt = OW; op.C = C2;
     op.Wt_ptr = w2->ptr; op.N = 32; op.taps = 9; op.kpad = (int)w2->shape[1] / 9;
