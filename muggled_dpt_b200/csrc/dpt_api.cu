@@ -324,6 +324,7 @@ struct GemmOp {
   void* out = nullptr;
   long long ldo = 0;                  // default N
   int OH = 0, OW = 0, so = 1, oy = 0, ox = 0;  // default OH = H, OW = W
+  int shuffle_n = 0;                  // merged ConvTranspose: N = so*so*shuffle_n (gemm_tc.cuh)
   const void* add1 = nullptr;
   long long ld_add1 = 0;
   const void* add2 = nullptr;
@@ -410,6 +411,11 @@ bool add_gemm(Ctx& c, GemmOp op) {
   p.out = op.out;
   p.ldo = op.ldo;
   p.OH = op.OH; p.OW = op.OW; p.so = op.so; p.oy = op.oy; p.ox = op.ox;
+  if (op.shuffle_n > 0) {
+    if (op.shuffle_n % bn != 0 || op.N != op.so * op.so * op.shuffle_n || op.out_kind != OUT_HALF)
+      return c.fail("gemm: merged pixel-shuffle needs BLOCK_N | channels");
+    p.shuffle_n = op.shuffle_n;
+  }
   p.add1 = op.add1; p.ld_add1 = op.ld_add1 ? op.ld_add1 : op.ldo;
   p.add2 = op.add2; p.ld_add2 = op.ld_add2 ? op.ld_add2 : op.ldo;
   p.out2_relu = op.out2_relu; p.ld_out2 = op.ld_out2 ? op.ld_out2 : op.ldo;
@@ -1177,6 +1183,16 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
       res = c.ar.alloc((size_t)B * rh * rw * R * 2);
       const long long rows_per_sub = uw->shape[0] / (s * s);
       const int kpad = (int)uw->shape[1];
+      // one launch when the channel count is a whole number of n-tiles (the tile then lies inside one sub-pixel block)
+      const int bn_merged = (s * s * R) > 128 ? 256 : pick_block_n(s * s * R);
+      if (R % bn_merged == 0 && R % 128 == 0) {
+        GemmOp op;
+        op.A = proj; op.B = B; op.Ht = gh; op.Wt = gw; op.C = R;
+        op.Wt_ptr = uw->ptr; op.N = s * s * R; op.kpad = kpad; op.ldo = R;
+        op.bias = (const float*)ub->ptr; op.out = res;
+        op.so = s; op.shuffle_n = R; op.OH = rh; op.OW = rw; op.label = "convT";
+        add_gemm(c, op);
+      } else
       for (int sub = 0; sub < s * s; ++sub) {
         GemmOp op;
         op.A = proj; op.B = B; op.Ht = gh; op.Wt = gw; op.C = R;

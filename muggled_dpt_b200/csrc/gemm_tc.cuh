@@ -50,6 +50,8 @@ struct __align__(64) GemmParams {
   void* out;
   long long ldo;      // elements between consecutive output pixels
   int OH, OW, so, oy, ox;
+  int shuffle_n;      // > 0: ConvTranspose2d(k = s = so) in ONE launch - the N axis is [so*so][shuffle_n]: n-tile n_blk
+                      // writes channels (n % shuffle_n) of sub-pixel (oy, ox) = divmod(n / shuffle_n, so); BLOCK_N | shuffle_n
   const void* add1;   // same dtype + pixel indexing as out (may alias out: in-place residual)
   long long ld_add1;
   const void* add2;
@@ -312,7 +314,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int x = tx * TW + (r & (TW - 1));
       const int y = ty * TH + (r >> p.tw_log2);
       const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
-      const long long pix = ((long long)b * p.OH + (long long)y * p.so + p.oy) * p.OW + (long long)x * p.so + p.ox;
+      // pixel-shuffle target: fixed per launch, or chosen by the n-tile (merged ConvTranspose)
+      const int sub_px = p.shuffle_n > 0 ? (n_blk * BLOCK_N) / p.shuffle_n : 0;
+      const int sh_oy = p.shuffle_n > 0 ? sub_px / p.so : p.oy, sh_ox = p.shuffle_n > 0 ? sub_px % p.so : p.ox;
+      const int n_base = p.shuffle_n > 0 ? n_blk * BLOCK_N - sub_px * p.shuffle_n : n_blk * BLOCK_N;  // channel of column 0
+      const long long pix = ((long long)b * p.OH + (long long)y * p.so + sh_oy) * p.OW + (long long)x * p.so + sh_ox;
 
       // folded LayerNorm: the partial statistics of my row; the loads are issued before the bias barriers below so
       // that their latency overlaps (ln_parts is even: two (sum, sum sq) pairs per 16-byte load)
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       if (et < BLOCK_N) {
         const int n = n_blk * BLOCK_N + et;
         const bool in = n < p.N && b < p.B;
-        bs[et] = (p.bias != nullptr && in) ? __ldg(p.bias + (long long)b * p.bias_bstride + n) : 0.0f;
+        bs[et] = (p.bias != nullptr && in) ? __ldg(p.bias + (long long)b * p.bias_bstride + (n_base + et)) : 0.0f;
         cs[et] = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n) : 0.0f;
       }
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
@@ -500,9 +506,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             __syncwarp();
             // ---- phase 2: coalesced global IO; 8 lanes cover one 128-byte row segment, 4 rows per pass, all
             //      eight passes' loads issued before the first store (the residual may alias the output)
-            const int ncol0 = n_blk * BLOCK_N + col_base + c0;  // first output column of this staging chunk
+            const int ncol0 = n_blk * BLOCK_N + col_base + c0;  // first GEMM column of this staging chunk
             const bool col_ok = (sub * ELEMS_PER_CHUNK < NCOLS_HERE) && (ncol0 + sub * ELEMS_PER_CHUNK) < p.N;
-            const long long coff = ncol0 + sub * ELEMS_PER_CHUNK;
+            const long long coff = n_base + col_base + c0 + sub * ELEMS_PER_CHUNK;  // output channel
             if constexpr (F32OUT) {
               const long long(&rpix)[8] = res_pix;
               bool ok[8];

@@ -248,6 +248,8 @@ STANDARD_CONFIGS = {
     "tiny": dict(F=128, blocks=4, reasm=(16, 32, 64, 128), C=32),
     # 8 blocks: the V1 tap rule (last four blocks) and the V2 rule (every second block) differ
     "tiny8": dict(F=128, blocks=8, reasm=(16, 32, 64, 128), C=32),
+    # wide reassembly channels on a small encoder: the ViT-L-sized ConvTranspose path (256 channels) at test cost
+    "tiny_r256": dict(F=128, blocks=4, reasm=(256, 256, 64, 128), C=32),
 }
 
 

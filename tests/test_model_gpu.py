@@ -128,6 +128,31 @@ def test_vits_504_against_oracle():
         assert e[2] < DEPTH_MAXREL[dtype], e
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_wide_reassembly_merged_conv_transpose_against_oracle(dtype):
+    """256 reassembly channels (the ViT-L case): ConvTranspose2d k=s=4 / k=s=2 run as ONE pixel-shuffling GEMM launch
+    each (gemm_tc.cuh shuffle_n) instead of s*s launches; checked per map against the fp32 oracle."""
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict("tiny_r256", seed=13, base_grid=5)
+    img = O.make_input(2, 56, 84, seed=3)
+    ref = O.forward(sd, img, return_stages=True)
+    cfg, model = _load_model(sd, dtype)
+    assert cfg["reassembly_features_list"] == [256, 256, 64, 128]
+    with torch.inference_mode():
+        grid = tuple(ref["grid_hw"])
+        maps = model.reassemble(*[t.to("cuda", dtype) for t in ref["taps"]], grid)
+        depth = model(img.to("cuda", dtype))
+    labels = [lab for lab, *_ in model.read_profile()] if False else None  # (launch labels are checked in bench tables)
+    for i in range(4):
+        assert tuple(maps[i].shape) == tuple(ref["maps"][i].shape)
+        e = _err(maps[i], ref["maps"][i])
+        print(f"tiny_r256 {dtype} map{i}: rel_l2={e[0]:.3e}")
+        assert e[0] < REL_L2[dtype], (i, e)
+    e = _err(depth, ref["depth"])
+    assert e[0] < 2 * REL_L2[dtype], e
+
+
 def test_properties_batch_independence_and_determinism():
     """size-independent properties: frames of a batch do not interact (dpt_model.py has no cross-batch op), and the
     path is deterministic run to run"""
