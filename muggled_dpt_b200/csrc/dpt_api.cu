@@ -681,7 +681,7 @@ bool build_patch_embed(Ctx& c, const void* img, void* tokens, int B, int H, int 
   if (!c.dry) {
     const int is_bf16 = c.is_bf16, nsm = c.num_sms;
     c.add("im2col_patch", 0.0, (double)B * 3 * H * W * 2.0 + (double)M * kpad * 2.0, [=](cudaStream_t s) {
-      const int grid = ew_grid(M * kpad, 256, nsm);
+      const int grid = ew_grid(M * kpad / 2, 256, nsm);
       DISPATCH_T(is_bf16, (im2col_patch_kernel<T><<<grid, 256, 0, s>>>((const T*)img, (T*)A, B, 3, H, W, P, gh, gw, kpad)));
       return cudaGetLastError();
     });

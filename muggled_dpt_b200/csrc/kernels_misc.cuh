@@ -19,27 +19,35 @@ template <typename T> struct __align__(16) Vec8 { T v[8]; };  // 16 bytes
 
 // ---------------------------------------------------------------------------------------------------------------
 // Patch-embed im2col (patch_embed.py:92-97): img [B,3,H,W] -> A [B*gh*gw, kpad], k = c*P*P + ky*P + kx, zero padded.
+// One thread per PAIR of horizontally adjacent image pixels: the reads are fully coalesced 4-byte loads of the NCHW
+// image; the two pixels land in the same patch row (P is even), 4 bytes apart in A. The zero padding of columns
+// [3*P*P, kpad) is written by the tail of the same grid-stride loop.
 template <typename T>
 __global__ void im2col_patch_kernel(const T* __restrict__ img, T* __restrict__ A, int B, int Cin, int H, int W, int P,
                                     int gh, int gw, int kpad) {
-  const long long total = (long long)B * gh * gw * kpad;
   const int kreal = Cin * P * P;
+  const int W2 = W >> 1;
+  const long long npairs = (long long)B * Cin * H * W2;
+  const long long M = (long long)B * gh * gw;
+  const int padw = (kpad - kreal) >> 1;  // zero pairs per row of A (kreal and kpad are even)
+  const long long total = npairs + M * padw;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % kpad);
-    const long long m = idx / kpad;
-    T v = from_f32<T>(0.0f);
-    if (k < kreal) {
-      const int c = k / (P * P);
-      const int rem = k - c * P * P;
-      const int ky = rem / P, kx = rem - ky * P;
-      const int px = (int)(m % gw);
-      const long long t = m / gw;
-      const int py = (int)(t % gh);
-      const int b = (int)(t / gh);
-      v = img[(((long long)b * Cin + c) * H + (py * P + ky)) * W + (px * P + kx)];
+    if (idx < npairs) {
+      const int x = (int)(idx % W2) * 2;
+      long long t = idx / W2;
+      const int y = (int)(t % H);
+      t /= H;
+      const int c = (int)(t % Cin);
+      const int b = (int)(t / Cin);
+      const int px = x / P, kx = x - px * P, py = y / P, ky = y - py * P;
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(img + idx * 2);
+      *reinterpret_cast<uint32_t*>(A + (((long long)b * gh + py) * gw + px) * kpad + (c * P + ky) * P + kx) = v;
+    } else {
+      const long long j = idx - npairs;
+      const long long m = j / padw;
+      *reinterpret_cast<uint32_t*>(A + m * kpad + kreal + (int)(j - m * padw) * 2) = 0u;
     }
-    A[idx] = v;
   }
 }
 
