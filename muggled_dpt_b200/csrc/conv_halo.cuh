@@ -14,11 +14,17 @@
 // 128-byte-aligned row-shifted view of a TMA-written tile reads back consistently (matrix-descriptor base_offset = 0;
 // setting it to the start's row phase gives wrong results). All nine taps' weights (9 x C x 32) stay resident in
 // shared memory for the life of the persistent CTA.
+//
+// FUSED_RESIZE: the convolution's input is the bilinear (align_corners=True) up-sampling of a smaller map
+// (head_model.py:95-101: conv -> interpolate x1.75 / x2 -> conv). Instead of reading the up-sampled map, four extra
+// "halo builder" warps interpolate each halo pixel from the source map (same arithmetic and 16-bit rounding as
+// resize_bilinear_ac_kernel) and write it into the stage with the swizzle applied by hand (16-byte chunk index
+// ^= pixel row & 7); the up-sampled map (2 GB written + read per ViT-L forward at batch 32) is never materialised.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "ptx.cuh"
-#include "gemm_tc.cuh"  // ACT_* , rcp_approx
+#include "gemm_tc.cuh"  // ACT_* , rcp_approx, pack2 / unpack2
 
 namespace dpt {
 
@@ -30,6 +36,8 @@ constexpr int HALO_N = 32;
 constexpr int HALO_W_TILE_BYTES = HALO_N * 128;  // weights of one (tap, 64-channel chunk): 4 096 B
 constexpr int HALO_MAX_KCHUNKS = 2;              // C <= 128
 constexpr int HALO_THREADS = 192;                // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int HALO_BUILDERS = 256;               // FUSED_RESIZE: warps 6..13 build the halo tiles
+constexpr int HALO_THREADS_FUSED = HALO_THREADS + HALO_BUILDERS;
 constexpr int HALO_SMEM_BYTES = HALO_STAGES * HALO_A_BYTES + 9 * HALO_MAX_KCHUNKS * HALO_W_TILE_BYTES + 256;
 
 struct __align__(64) HaloParams {
@@ -44,6 +52,9 @@ struct __align__(64) HaloParams {
   float head_b;
   int head_act;     // ACT_RELU or ACT_SIGMOID
   void* out;        // [B, H, W] 16-bit
+  // FUSED_RESIZE: source map [B, IH, IW, C] 16-bit; the convolution runs on its bilinear resize to H x W
+  const void* src;
+  int IH, IW, C;
 };
 
 // K-major SWIZZLE_128B descriptor with explicit stride between 8-row groups and swizzle phase of the first row
@@ -58,8 +69,9 @@ DPT_DEVICE uint64_t make_smem_desc_sw128_ex(uint32_t smem_addr, uint32_t sbo_byt
   return d;
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(HALO_THREADS, 1) conv3x3_halo_head_kernel(const __grid_constant__ HaloParams p) {
+template <bool BF16, bool FUSED_RESIZE = false>
+__global__ void __launch_bounds__(FUSED_RESIZE ? HALO_THREADS_FUSED : HALO_THREADS, 1)
+    conv3x3_halo_head_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + HALO_STAGES * HALO_A_BYTES;
@@ -80,10 +92,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv3x3_halo_head_kernel(cons
       printf("dpt conv_halo: dynamic smem base not 1024-aligned\n");
       __trap();
     }
-    prefetch_tmap(&p.tmA);
+    if (!FUSED_RESIZE) prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
     for (int i = 0; i < HALO_STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], FUSED_RESIZE ? HALO_BUILDERS : 1);
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(w_full, 1);
@@ -115,7 +127,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv3x3_halo_head_kernel(cons
                       (tap * p.kchunks + kc) * 64, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; !FUSED_RESIZE && tile < total_tiles; tile += gridDim.x) {
         int t = tile;
         const int tx = t % p.tiles_x;
         t /= p.tiles_x;
@@ -165,6 +177,112 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv3x3_halo_head_kernel(cons
       }
     }
     __syncwarp();
+  } else if (FUSED_RESIZE && warp_idx >= 6) {
+    // ===================================== halo builders =====================================
+    const int bt = threadIdx.x - HALO_THREADS;  // 0..127
+    const int ch = bt & 7;                      // 16-byte chunk (8 channels) of a pixel's 128-byte row
+    const float sy = p.H > 1 ? (float)(p.IH - 1) / (float)(p.H - 1) : 0.0f;
+    const float sx = p.W > 1 ? (float)(p.IW - 1) / (float)(p.W - 1) : 0.0f;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(p.src);
+    constexpr int is_bf16 = BF16 ? 1 : 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int b = t / p.tiles_y;
+      const size_t img_off = (size_t)b * p.IH * p.IW * p.C;
+      {
+        // The source map was written by the previous kernel and is larger than L2: first touches are DRAM latency.
+        // Pull the source footprint of the tile this CTA builds HALO_PF tiles from now into L2 (one line per thread).
+        constexpr int HALO_PF = 3;
+        const int tn = tile + HALO_PF * (int)gridDim.x;
+        if (tn < total_tiles) {
+          int t2 = tn;
+          const int ntx = t2 % p.tiles_x;
+          t2 /= p.tiles_x;
+          const int nty = t2 % p.tiles_y;
+          const int nb = t2 / p.tiles_y;
+          const int ys = max((int)(sy * (nty * HALO_TH - 1)), 0), xs = max((int)(sx * (ntx * HALO_TW - 1)), 0);
+          const int ye = min((int)(sy * (nty * HALO_TH + HALO_TH)) + 1, p.IH - 1);
+          const int xe = min((int)(sx * (ntx * HALO_TW + HALO_TW)) + 1, p.IW - 1);
+          const int wpx = xe - xs + 1, npx = wpx * (ye - ys + 1);
+          const int lines_per_px = (p.C * 2 + 127) / 128;
+          for (int i = bt; i < npx * lines_per_px; i += HALO_BUILDERS) {
+            const int px = i / lines_per_px, ln = i - px * lines_per_px;
+            const int yy = ys + px / wpx, xx = xs + px % wpx;
+            const uint16_t* a = src + (size_t)nb * p.IH * p.IW * p.C + ((size_t)yy * p.IW + xx) * p.C + ln * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        }
+      }
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t stage = smem_u32(sA + s * HALO_A_BYTES);
+        const int c0 = kc * 64 + ch * 8;
+        // 180 pixels x 8 chunks = 1440 tasks per stage, 256 threads: rounds of NB tasks per thread with all 4*NB source
+        // loads of a round in flight before the first use (the source footprint of a tile is ~10 KB: L1 hits)
+        constexpr int NB = 3;
+        constexpr int PIX_STEP = HALO_BUILDERS / 8;  // 32 pixels between a thread's consecutive tasks
+#pragma unroll 1
+        for (int pix0 = bt >> 3; pix0 < HALO_PW * HALO_PH; pix0 += NB * PIX_STEP) {
+          uint4 v[NB][4];
+          float ly[NB], lx[NB];
+          bool ok[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int pix = pix0 + i * PIX_STEP;
+            const int py = pix / HALO_PW, px = pix - py * HALO_PW;
+            const int oy = ty * HALO_TH - 1 + py, ox = tx * HALO_TW - 1 + px;
+            ok[i] = pix < HALO_PW * HALO_PH && oy >= 0 && oy < p.H && ox >= 0 && ox < p.W && c0 < p.C;
+            if (ok[i]) {
+              const float fy = sy * oy, fx = sx * ox;
+              const int y0 = min((int)fy, p.IH - 1), x0 = min((int)fx, p.IW - 1);
+              const int y1 = min(y0 + 1, p.IH - 1), x1 = min(x0 + 1, p.IW - 1);
+              ly[i] = fy - y0;
+              lx[i] = fx - x0;
+              const uint16_t* base = src + img_off + c0;
+              v[i][0] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * p.IW + x0) * p.C));
+              v[i][1] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * p.IW + x1) * p.C));
+              v[i][2] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * p.IW + x0) * p.C));
+              v[i][3] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * p.IW + x1) * p.C));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int pix = pix0 + i * PIX_STEP;
+            if (pix >= HALO_PW * HALO_PH) break;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);  // zero padding outside the map / past the channel count
+            if (ok[i]) {
+              const float hy = 1.0f - ly[i], hx = 1.0f - lx[i];
+              const uint32_t* a = reinterpret_cast<const uint32_t*>(&v[i][0]);
+              const uint32_t* bq = reinterpret_cast<const uint32_t*>(&v[i][1]);
+              const uint32_t* cq = reinterpret_cast<const uint32_t*>(&v[i][2]);
+              const uint32_t* d = reinterpret_cast<const uint32_t*>(&v[i][3]);
+              uint32_t r[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f00 = unpack2(a[k], is_bf16), f01 = unpack2(bq[k], is_bf16);
+                const float2 f10 = unpack2(cq[k], is_bf16), f11 = unpack2(d[k], is_bf16);
+                // same expression as resize_bilinear_ac_kernel: hy * (hx v00 + lx v01) + ly * (hx v10 + lx v11)
+                const float rx = hy * (hx * f00.x + lx[i] * f01.x) + ly[i] * (hx * f10.x + lx[i] * f11.x);
+                const float ry = hy * (hx * f00.y + lx[i] * f01.y) + ly[i] * (hx * f10.y + lx[i] * f11.y);
+                r[k] = pack2(rx, ry, is_bf16);
+              }
+              o = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+            // 128-byte swizzle by hand: the chunk index is XORed with address bits [7,10) = pixel row & 7
+            const uint32_t dst = stage + pix * 128 + ((ch ^ (pix & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&full_bar[s]);
+        if (++s == HALO_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
   } else {
     // ===================================== epilogue =====================================
     const int q = warp_idx & 3;                 // TMEM lane quarter of this warp

@@ -463,25 +463,44 @@ bool halo_enabled() {
   return v != 0;
 }
 
-template <bool BF16>
+// DPT_HALO_FUSE=1: do not materialise the up-sampled map; the halo kernel's builder warps interpolate each tile from
+// the source map (conv_halo.cuh FUSED_RESIZE). Same results (tests/test_model_gpu.py runs it in a subprocess), but
+// measured slower on ViT-L B=32: 3.1 ms against 0.64 ms (resize) + 1.2 ms (TMA-fed halo conv) - the builders are bound by
+// the latency of their dependent load -> interpolate -> st.shared rounds, not by DRAM (an L2 prefetch of the source
+// footprint three tiles ahead changed nothing). Off by default.
+bool halo_fuse_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_HALO_FUSE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+template <bool BF16, bool FUSED>
 cudaError_t launch_halo_inst(const HaloParams& p, int grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_head_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_head_kernel<BF16, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HALO_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_ex(conv3x3_halo_head_kernel<BF16>, dim3((unsigned)grid), dim3(HALO_THREADS), HALO_SMEM_BYTES, s, false, p);
+  return launch_ex(conv3x3_halo_head_kernel<BF16, FUSED>, dim3((unsigned)grid),
+                   dim3(FUSED ? HALO_THREADS_FUSED : HALO_THREADS), HALO_SMEM_BYTES, s, false, p);
 }
 
-// in [B, H, W, C] 16-bit (C <= 128), Wt [32, 9 * kpad], out [B, H, W]
+// in [B, H, W, C] 16-bit (C <= 128), Wt [32, 9 * kpad], out [B, H, W]. src != nullptr: `in` is not read; the input is
+// the bilinear (align_corners=True) resize of src [B, IH, IW, C] to H x W, built tile by tile inside the kernel.
 bool add_conv_halo_head(Ctx& c, const void* in, const void* Wt, int kpad, const float* bias, const float* head_w,
-                        float head_b, int head_act, void* out, int B, int H, int W, int C, const char* label) {
+                        float head_b, int head_act, void* out, int B, int H, int W, int C, const char* label,
+                        const void* src = nullptr, int IH = 0, int IW = 0) {
   if (c.dry) return true;
   HaloParams p;
   memset(&p, 0, sizeof p);
-  {
+  const bool fused = src != nullptr;
+  p.src = src; p.IH = IH; p.IW = IW; p.C = C;
+  if (!fused) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H};
     uint32_t box[4] = {64, HALO_PW, HALO_PH, 1};
@@ -507,9 +526,12 @@ bool add_conv_halo_head(Ctx& c, const void* in, const void* Wt, int kpad, const 
   const int grid = (int)std::min<long long>(total, c.num_sms);
   const double pix = (double)B * H * W;
   const int is_bf16 = c.is_bf16;
-  c.add(std::string("conv_halo32:") + c.scope + label, 2.0 * pix * HALO_N * C * 9,
-        pix * C * 2.0 + 9.0 * kpad * HALO_N * 2.0 + pix * 2.0,
-        [p, grid, is_bf16](cudaStream_t s) { return is_bf16 ? launch_halo_inst<true>(p, grid, s) : launch_halo_inst<false>(p, grid, s); });
+  const double in_bytes = fused ? (double)B * IH * IW * C * 2.0 : pix * C * 2.0;
+  c.add(std::string(fused ? "resize_conv_halo32:" : "conv_halo32:") + c.scope + label, 2.0 * pix * HALO_N * C * 9,
+        in_bytes + 9.0 * kpad * HALO_N * 2.0 + pix * 2.0, [p, grid, is_bf16, fused](cudaStream_t s) {
+          if (fused) return is_bf16 ? launch_halo_inst<true, true>(p, grid, s) : launch_halo_inst<false, true>(p, grid, s);
+          return is_bf16 ? launch_halo_inst<true, false>(p, grid, s) : launch_halo_inst<false, false>(p, grid, s);
+        });
   return true;
 }
 
@@ -1335,8 +1357,11 @@ bool build_head(Ctx& c, const void* fused, void* depth, int B, int h, int w) {
   if (!c.ok) return false;
   const int C2 = (int)w1->shape[0];
   const size_t mk = c.ar.mark();
+  const int kpad2 = (int)w2->shape[1] / 9;
+  const bool use_halo = halo_enabled() && (int)w2->shape[0] == HALO_N && kpad2 <= 64 * HALO_MAX_KCHUNKS && C2 % 8 == 0;
+  const bool fuse_resize = use_halo && halo_fuse_enabled();  // the up-sampled map is never materialised
   void* h1 = c.ar.alloc((size_t)B * h * w * C2 * 2);
-  void* h2 = c.ar.alloc((size_t)B * OH * OW * C2 * 2);
+  void* h2 = fuse_resize ? nullptr : c.ar.alloc((size_t)B * OH * OW * C2 * 2);
   {
     GemmOp op;
     op.A = fused; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
@@ -1345,12 +1370,12 @@ bool build_head(Ctx& c, const void* fused, void* depth, int B, int h, int w) {
     c.scope = "head.";
     add_gemm(c, op);
   }
-  add_resize(c, h1, h2, B, h, w, OH, OW, C2);
-  const int kpad2 = (int)w2->shape[1] / 9;
-  if (halo_enabled() && (int)w2->shape[0] == HALO_N && kpad2 <= 64 * HALO_MAX_KCHUNKS && C2 % 8 == 0) {
+  if (!fuse_resize) add_resize(c, h1, h2, B, h, w, OH, OW, C2);
+  if (use_halo) {
     c.scope = "head.";
     add_conv_halo_head(c, h2, w2->ptr, kpad2, (const float*)b2->ptr, (const float*)w3->ptr, *(const float*)b3->ptr,
-                       cfg.is_metric ? ACT_SIGMOID : ACT_RELU, depth, B, OH, OW, C2, "c2c3");
+                       cfg.is_metric ? ACT_SIGMOID : ACT_RELU, depth, B, OH, OW, C2, "c2c3",
+                       fuse_resize ? h1 : nullptr, h, w);
   } else {
     GemmOp op;
     op.A = h2; op.B = B; op.Ht = OH; op.Wt = OW; op.C = C2;

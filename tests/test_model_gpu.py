@@ -153,6 +153,39 @@ def test_wide_reassembly_merged_conv_transpose_against_oracle(dtype):
     assert e[0] < 2 * REL_L2[dtype], e
 
 
+def test_head_variants_fused_resize_and_generic_conv_agree_with_default():
+    """The head's second convolution has three implementations selected by environment switches read once per
+    process: the default TMA-fed halo kernel, DPT_HALO_FUSE=1 (halo tiles interpolated inside the kernel, the up-sampled
+    map never materialised) and DPT_HALO=0 (generic nine-load spatial GEMM). All must match the oracle."""
+    import subprocess
+    import sys
+
+    code = (
+        "import os, sys, tempfile, torch\n"
+        "sys.path.insert(0, os.getcwd())\n"
+        "from muggled_dpt_b200 import make_dpt_from_state_dict\n"
+        "from oracle import dpt_oracle as O\n"
+        "for name, seed, hw in (('tiny', 3, (56, 84)), ('vits', 11, (112, 140))):\n"
+        "    sd = O.make_synthetic_state_dict(name, seed=seed, base_grid=5 if name == 'tiny' else 37)\n"
+        "    img = O.make_input(2, hw[0], hw[1], seed=5)\n"
+        "    ref = O.forward(sd, img)\n"
+        "    with tempfile.TemporaryDirectory() as td:\n"
+        "        p = os.path.join(td, 'depth_anything_v2_x.pth'); torch.save(sd, p)\n"
+        "        _, m = make_dpt_from_state_dict(p)\n"
+        "    m.to(device='cuda', dtype=torch.float16)\n"
+        "    out = m(img.to('cuda', torch.float16)).float().cpu()\n"
+        "    e = ((out - ref).norm() / ref.norm()).item()\n"
+        "    print(name, 'rel_l2', e)\n"
+        "    assert e < 3e-3, e\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env_extra in ({"DPT_HALO_FUSE": "1"}, {"DPT_HALO": "0"}):
+        env = dict(os.environ, **env_extra)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        print(env_extra, r.stdout.strip().replace("\n", " | "))
+        assert r.returncode == 0, (env_extra, r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_properties_batch_independence_and_determinism():
     """size-independent properties: frames of a batch do not interact (dpt_model.py has no cross-batch op), and the
     path is deterministic run to run"""
