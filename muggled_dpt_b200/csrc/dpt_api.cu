@@ -216,11 +216,11 @@ cudaError_t launch_gemm_inst(const GemmParams& p, int grid, cudaStream_t s) {
                    GemmCfg<BN, false, RESPF>::SMEM_BYTES, s, false, p);
 }
 
-// 2-CTA (cta_group::2) variant: BLOCK_N = 256, launched as clusters of two CTAs
-template <int OUT_KIND, int ACT, bool BF16, bool RESPF = false>
+// 2-CTA (cta_group::2) variant: BLOCK_N = 256 (or 128 for the 16-bit-output convolutions), clusters of two CTAs
+template <int OUT_KIND, int ACT, bool BF16, bool RESPF = false, int BN = 256>
 cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<256, OUT_KIND, ACT, BF16, true, RESPF>;
-  constexpr int smem = GemmCfg<256, true, RESPF>::SMEM_BYTES;
+  auto kern = gemm_tc_kernel<BN, OUT_KIND, ACT, BF16, true, RESPF>;
+  constexpr int smem = GemmCfg<BN, true, RESPF>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -231,7 +231,11 @@ cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
 }
 
 template <bool BF16>
-cudaError_t launch_gemm2_dt(const GemmParams& p, int grid, cudaStream_t s) {
+cudaError_t launch_gemm2_dt(const GemmParams& p, int bn, int grid, cudaStream_t s) {
+  if (bn == 128) {  // (chosen only for 16-bit outputs without GELU, see add_gemm)
+    if (p.act == ACT_RELU) return launch_gemm2_inst<OUT_HALF, ACT_RELU, BF16, false, 128>(p, grid, s);
+    return launch_gemm2_inst<OUT_HALF, ACT_NONE, BF16, false, 128>(p, grid, s);
+  }
   if (p.out_kind == OUT_F32)
     return use_respf(p) ? launch_gemm2_inst<OUT_F32, ACT_NONE, BF16, true>(p, grid, s)
                         : launch_gemm2_inst<OUT_F32, ACT_NONE, BF16>(p, grid, s);
@@ -262,7 +266,7 @@ cudaError_t launch_gemm_dt(const GemmParams& p, int bn, int grid, cudaStream_t s
 }
 
 cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, bool two_cta, cudaStream_t s) {
-  if (two_cta) return p.is_bf16 ? launch_gemm2_dt<true>(p, grid, s) : launch_gemm2_dt<false>(p, grid, s);
+  if (two_cta) return p.is_bf16 ? launch_gemm2_dt<true>(p, bn, grid, s) : launch_gemm2_dt<false>(p, bn, grid, s);
   return p.is_bf16 ? launch_gemm_dt<true>(p, bn, grid, s) : launch_gemm_dt<false>(p, bn, grid, s);
 }
 
@@ -377,6 +381,11 @@ bool add_gemm(Ctx& c, GemmOp op) {
     const TileChoice tc = choose_tile(m_tiles_all, op.N, c.num_sms);
     bn = tc.bn;
     two_cta = tc.two_cta;
+  } else if (bn == 128 && op.taps == 9 && op.out_kind == OUT_HALF && op.act != ACT_GELU && two_cta_enabled() &&
+             gemm_mode() == 0 && (m_tiles_all + 1) / 2 >= 4 * (c.num_sms / 2)) {
+    // 128-wide 3x3 convolutions (head c1) are bound by L2 -> SM operand traffic: CTA pairs on 256 x 128 tiles stage
+    // half of the weight tile each, a quarter less traffic per FLOP
+    two_cta = true;
   }
 
   {
@@ -446,7 +455,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
     if (op.add2) bytes += pix * op.N * 2.0;
     if (op.out2_relu) bytes += pix * op.N * 2.0;
     if (op.out16) bytes += pix * op.N * 2.0;
-    c.add(std::string(two_cta ? "gemm256x2" : "gemm" + std::to_string(bn)) + ":" + c.scope + op.label, flops, bytes,
+    c.add(std::string("gemm") + std::to_string(bn) + (two_cta ? "x2" : "") + ":" + c.scope + op.label, flops, bytes,
           [p, bn, grid, two_cta](cudaStream_t s) { return launch_gemm(p, bn, grid, two_cta, s); });
   }
   return true;

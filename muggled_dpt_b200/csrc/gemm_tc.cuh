@@ -83,7 +83,7 @@ struct __align__(64) GemmParams {
 // residual of the next 32-column unit - and pay for it with one pipeline stage.
 template <int BLOCK_N, bool TWO_CTA = false, bool F32OUT = false>
 struct GemmCfg {
-  static constexpr int STAGES_BASE = TWO_CTA ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int STAGES_BASE = TWO_CTA ? (BLOCK_N == 256 ? 6 : 8) : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int STAGES = !F32OUT ? STAGES_BASE : (BLOCK_N == 64 ? 6 : (BLOCK_N == 32 ? 8 : STAGES_BASE - 1));
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = (TWO_CTA ? BLOCK_N / 2 : BLOCK_N) * GEMM_BLOCK_K * 2;
@@ -153,7 +153,7 @@ template <int BLOCK_N, int OUT_KIND, int ACT, bool BF16, bool TWO_CTA = false, b
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   static_assert(!RESPF || OUT_KIND == OUT_F32, "residual prefetch exists for fp32 outputs only");
   using Cfg = GemmCfg<BLOCK_N, TWO_CTA, RESPF>;
-  static_assert(!TWO_CTA || BLOCK_N == 256, "the 2-CTA kernel is built for BLOCK_N = 256");
+  static_assert(!TWO_CTA || BLOCK_N == 256 || BLOCK_N == 128, "the 2-CTA kernel is built for BLOCK_N = 256 and 128");
   constexpr int STAGES = Cfg::STAGES;
 
   // no static shared memory in this kernel: the dynamic segment starts at the CTA's (1024-aligned) window base;

@@ -244,6 +244,22 @@ def test_gemm_two_cta_f32_residual_inplace():
     assert rel < 1e-3, (rel, mx)
 
 
+def test_conv3x3_two_cta_pairs_128_wide():
+    """N = 128 convolution large enough (>= 296 tile pairs) for the 256 x 128 CTA-pair kernel (head c1 at full size)"""
+    from gpu_util import conv_gemm, rel_err
+
+    B, H, W, C, N = 2, 200, 200, 64, 128   # 2 * 13 * 25 = 650 M-tiles of 8 x 16 / 16 x 8 pixels
+    x = _mk((B, H, W, C), torch.bfloat16, 58)
+    w = _mk((N, C, 3, 3), torch.bfloat16, 59, (9 * C) ** -0.5)
+    bias = _mk((N,), torch.float32, 60)
+    for act in (0, 2):
+        out = conv_gemm(x, pack_conv(w), bias, taps=9, act=act)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+        ref = F.relu(ref) if act == 2 else ref
+        rel, mx = rel_err(out, ref)
+        assert rel < 6e-3, (act, rel, mx)
+
+
 def test_conv3x3_two_cta_pairs():
     from gpu_util import conv_gemm, rel_err
 
