@@ -8,13 +8,18 @@
 //   (out-of-bounds rows/columns are zero-filled by the TMA unit == zero padding). Token matrices [M, K] are the
 //   degenerate case H = 1, TW = 128; "drop the cls token" is xoff = 1 on a (F, N, 1, B) map.
 // * Wt is [N, taps*kpad] K-major (nn.Linear / packed conv weights), loaded by a 2-D TMA map.
-// * tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16, bf16/fp16 -> fp32) accumulates in TMEM, double-buffered so
-//   the epilogue of tile i overlaps the main loop of tile i+1. Persistent CTAs, static round-robin tile schedule.
+// * tcgen05.mma (M=128, N=BLOCK_N, K=16, bf16/fp16 -> fp32; cta_group::2 CTA pairs on 256 x 256 / 256 x 128 tiles for
+//   the large launches) accumulates in TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile
+//   i+1. Persistent CTAs, static round-robin tile schedule.
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two warpgroups, each
 //   owning half of the accumulator columns; a warp can only read TMEM lanes 32*(warp%4)..+31).
 // * Epilogue: TMEM -> regs -> (+bias, GELU/ReLU) -> swizzled smem staging -> coalesced 16-byte global IO with optional
 //   residual / skip addends, optional second ReLU'd copy, fp32 or 16-bit output, output pixel remap
-//   (y*so+oy, x*so+ox) for pixel-shuffle (ConvTranspose) stores; "head" mode reduces 32 channels to one depth value.
+//   (y*so+oy, x*so+ox) for pixel-shuffle (ConvTranspose) stores - the sub-pixel either fixed per launch or picked by
+//   the n-tile (shuffle_n: one launch per ConvTranspose); "head" mode reduces 32 channels to one depth value.
+// * Folded LayerNorm (pre-norm transformer blocks): the consumer applies per-row (rstd, mean) and per-column weight
+//   sums in its epilogue, the fp32-output producer writes the per-row partial statistics and a 16-bit copy of the
+//   residual stream (GemmParams ln_* / stats_out / out16); RESPF: cp.async prefetch of the fp32 residual for short K.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
