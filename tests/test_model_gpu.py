@@ -143,7 +143,6 @@ def test_wide_reassembly_merged_conv_transpose_against_oracle(dtype):
         grid = tuple(ref["grid_hw"])
         maps = model.reassemble(*[t.to("cuda", dtype) for t in ref["taps"]], grid)
         depth = model(img.to("cuda", dtype))
-    labels = [lab for lab, *_ in model.read_profile()] if False else None  # (launch labels are checked in bench tables)
     for i in range(4):
         assert tuple(maps[i].shape) == tuple(ref["maps"][i].shape)
         e = _err(maps[i], ref["maps"][i])
