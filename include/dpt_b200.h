@@ -98,6 +98,15 @@ int dpt_prepare_image(const uint8_t* bgr_hwc, int IH, int IW, void* out_chw, int
 int dpt_postprocess_u8(const void* depth_bhw, int B, int H, int W, uint8_t* out_u8, int OH, int OW, float* minmax,
                        int dtype, void* stream);
 
+/* multi-GPU: the ONE collective of the path - every rank contributes its [B/G, H, W] shard of
+ * depth maps, every rank receives [B, H, W]. `nccl_comm` is the caller's ncclComm_t (one process per GPU); the call
+ * enqueues ncclAllGather on `stream` and returns. NCCL is resolved at run time from the process (the library does not
+ * link it: a PyTorch host already carries one); DPT_ERR_UNSUPPORTED when no NCCL is loaded or loadable. The Python
+ * host normally issues the same collective through torch.distributed (muggled_dpt_b200/distributed.py), which owns the
+ * communicator there. */
+int dpt_allgather_depth(void* nccl_comm, const void* local_depth, void* global_depth, size_t elems_per_rank, int dtype,
+                        void* stream);
+
 /* per-stage entry points (reference contract: simple_examples/internal_features.py:38-44) ------------------------ */
 /* PatchEmbed.forward (v2_depthanything/patch_embed.py:77-99): img -> tokens [B, gh*gw, F] 16-bit */
 int dpt_patch_embed(dpt_handle h, const void* img_bchw, void* tokens, void* workspace, size_t workspace_bytes, int B,

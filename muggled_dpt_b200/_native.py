@@ -71,6 +71,7 @@ SYMBOLS = [
     ("dpt_op_resize_bilinear", _I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     ("dpt_prepare_image", _I, [_VP, _I, _I, _VP, _I, _I, C.POINTER(_F * 3), C.POINTER(_F * 3), _I, _VP]),
     ("dpt_postprocess_u8", _I, [_VP, _I, _I, _I, _VP, _I, _I, _VP, _I, _VP]),
+    ("dpt_allgather_depth", _I, [_VP, _VP, _VP, _SZ, _I, _VP]),
     ("dpt_op_last_error", C.c_char_p, []),
     ("dpt_last_launch_count", _I, [_VP]),
     ("dpt_profile_enable", _I, [_VP, _I]),

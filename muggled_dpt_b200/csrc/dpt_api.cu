@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "dpt_b200.h"
+#include <dlfcn.h>
 #include "attn_tc.cuh"
 #include "conv_halo.cuh"
 #include "gemm_tc.cuh"
@@ -1781,6 +1782,36 @@ int dpt_postprocess_u8(const void* depth_bhw, int B, int H, int W, uint8_t* out_
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     g_err = std::string("dpt_postprocess_u8: ") + cudaGetErrorString(e);
+    return DPT_ERR_CUDA;
+  }
+  return DPT_OK;
+}
+
+int dpt_allgather_depth(void* nccl_comm, const void* local_depth, void* global_depth, size_t elems_per_rank, int dtype,
+                        void* stream) {
+  if (!nccl_comm || !local_depth || !global_depth || elems_per_rank == 0 || (dtype != DPT_BF16 && dtype != DPT_F16)) {
+    g_err = "dpt_allgather_depth: bad argument";
+    return DPT_ERR_INVALID;
+  }
+  // ncclResult_t ncclAllGather(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)
+  using AllGatherFn = int (*)(const void*, void*, size_t, int, void*, cudaStream_t);
+  static AllGatherFn fn = nullptr;
+  if (!fn) {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");  // the NCCL the host process already loaded (e.g. PyTorch's)
+    if (!sym) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) sym = dlsym(h, "ncclAllGather");
+    }
+    fn = reinterpret_cast<AllGatherFn>(sym);
+  }
+  if (!fn) {
+    g_err = "dpt_allgather_depth: no NCCL in this process (ncclAllGather not found)";
+    return DPT_ERR_UNSUPPORTED;
+  }
+  const int nccl_dtype = dtype == DPT_BF16 ? 9 /* ncclBfloat16 */ : 6 /* ncclFloat16 */;
+  const int rc = fn(local_depth, global_depth, elems_per_rank, nccl_dtype, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) {
+    g_err = "dpt_allgather_depth: ncclAllGather failed with ncclResult_t " + std::to_string(rc);
     return DPT_ERR_CUDA;
   }
   return DPT_OK;

@@ -37,3 +37,11 @@ def test_config_struct_layout_matches_header():
 
     # 14 ints + 1 float + 14 ints (SwinV2 block) + taps_last4 + mlp_swiglu, no padding
     assert ctypes.sizeof(N.DptConfig) == 31 * 4
+
+
+def test_allgather_entry_rejects_bad_arguments_without_gpu():
+    from muggled_dpt_b200 import _native as N
+
+    L = N.lib()
+    assert L.dpt_allgather_depth(None, None, None, 0, N.DPT_BF16, None) == -1  # DPT_ERR_INVALID
+    assert b"dpt_allgather_depth" in L.dpt_op_last_error()
