@@ -227,7 +227,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("DPT_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep whatever NCCL_DEBUG the caller / driver exported (its rank + topology lines verify the multi-GPU run);
+        # NCCL writes its log to stdout by default: send it to stderr so stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("DPT_NCCL_DEBUG", "WARN"))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16

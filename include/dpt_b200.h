@@ -68,6 +68,7 @@ int dpt_create(const dpt_config* cfg, dpt_handle* out);
 void dpt_destroy(dpt_handle h);
 const char* dpt_last_error(dpt_handle h);
 const char* dpt_version(void);
+int dpt_config_size(void); /* sizeof(dpt_config) the library was compiled with: lets a binding check its struct */
 
 /* weights: replaces nn.Module.load_state_dict of the five sub-models (make_depthanythingv2_dpt.py:55-59).
  * `name` is a packed-weight name (see muggled_dpt_b200/weights.py); the pointer must stay valid for the handle's

@@ -56,6 +56,7 @@ SYMBOLS = [
     ("dpt_destroy", None, [_VP]),
     ("dpt_last_error", C.c_char_p, [_VP]),
     ("dpt_version", C.c_char_p, []),
+    ("dpt_config_size", _I, []),
     ("dpt_set_weight", _I, [_VP, C.c_char_p, _VP, C.POINTER(C.c_int64), _I, _I]),
     ("dpt_workspace_bytes", _I, [_VP, _I, _I, _I, C.POINTER(_SZ)]),
     ("dpt_forward", _I, [_VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP]),

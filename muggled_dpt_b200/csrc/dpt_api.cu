@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -16,6 +17,7 @@
 #include "dpt_b200.h"
 #include <dlfcn.h>
 #include "attn_tc.cuh"
+#include "attn64_tc.cuh"
 #include "conv_halo.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_misc.cuh"
@@ -198,6 +200,39 @@ cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) belongs to the device's primary context: a kernel has to be opted in
+// once per DEVICE, not once per process (two models on two GPUs of one process share these statics).
+cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, uint64_t> done;  // kernel -> bit mask of devices already opted in
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  uint64_t& mask = done[kern];
+  if (dev >= 0 && dev < 64 && ((mask >> dev) & 1)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) mask |= uint64_t(1) << dev;
+  return e;
+}
+
+// Entry points that take a handle run on the handle's device whatever the caller's current device is.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 int pick_block_n(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
 // the residual-prefetch variant of the fp32-output kernels (gemm_tc.cuh RESPF) is used for short K loops
@@ -205,14 +240,9 @@ bool use_respf(const GemmParams& p) { return p.out_kind == OUT_F32 && p.add1 != 
 
 template <int BN, int OUT_KIND, int ACT, bool BF16, bool RESPF = false>
 cudaError_t launch_gemm_inst(const GemmParams& p, int grid, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16, false, RESPF>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<BN, false, RESPF>::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = ensure_dyn_smem((const void*)gemm_tc_kernel<BN, OUT_KIND, ACT, BF16, false, RESPF>,
+                                  GemmCfg<BN, false, RESPF>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   return launch_ex(gemm_tc_kernel<BN, OUT_KIND, ACT, BF16, false, RESPF>, dim3((unsigned)grid), dim3(GEMM_THREADS),
                    GemmCfg<BN, false, RESPF>::SMEM_BYTES, s, false, p);
 }
@@ -222,12 +252,8 @@ template <int OUT_KIND, int ACT, bool BF16, bool RESPF = false, int BN = 256>
 cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
   auto kern = gemm_tc_kernel<BN, OUT_KIND, ACT, BF16, true, RESPF>;
   constexpr int smem = GemmCfg<BN, true, RESPF>::SMEM_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = ensure_dyn_smem((const void*)kern, smem);
+  if (e != cudaSuccess) return e;
   return launch_ex(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), smem, s, true, p);
 }
 
@@ -489,13 +515,8 @@ bool halo_fuse_enabled() {
 
 template <bool BF16, bool FUSED>
 cudaError_t launch_halo_inst(const HaloParams& p, int grid, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_head_kernel<BF16, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         HALO_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = ensure_dyn_smem((const void*)conv3x3_halo_head_kernel<BF16, FUSED>, HALO_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   return launch_ex(conv3x3_halo_head_kernel<BF16, FUSED>, dim3((unsigned)grid),
                    dim3(FUSED ? HALO_THREADS_FUSED : HALO_THREADS), HALO_SMEM_BYTES, s, false, p);
 }
@@ -547,18 +568,36 @@ bool add_conv_halo_head(Ctx& c, const void* in, const void* Wt, int kpad, const 
 
 template <bool HAS_BIAS, bool BF16, int HD>
 cudaError_t launch_attn_inst(const AttnParams& p, dim3 grid, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<HAS_BIAS, BF16, HD>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = ensure_dyn_smem((const void*)attn_tc_kernel<HAS_BIAS, BF16, HD>, ATT_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   return launch_ex(attn_tc_kernel<HAS_BIAS, BF16, HD>, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, s, false, p);
 }
 template <bool HAS_BIAS, int HD>
 cudaError_t launch_attn(const AttnParams& p, dim3 grid, cudaStream_t s) {
   return p.is_bf16 ? launch_attn_inst<HAS_BIAS, true, HD>(p, grid, s) : launch_attn_inst<HAS_BIAS, false, HD>(p, grid, s);
+}
+
+// second-generation kernel (attn64_tc.cuh): 64-column kv steps, four CTAs per SM
+template <bool HAS_BIAS, bool BF16, int HD>
+cudaError_t launch_attn64_inst(const AttnParams& p, unsigned grid, cudaStream_t s) {
+  cudaError_t e = ensure_dyn_smem((const void*)attn64_tc_kernel<HAS_BIAS, BF16, HD>, A2_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return launch_ex(attn64_tc_kernel<HAS_BIAS, BF16, HD>, dim3(grid), dim3(A2_THREADS), A2_SMEM_BYTES, s, false, p);
+}
+template <bool HAS_BIAS, int HD>
+cudaError_t launch_attn64(const AttnParams& p, unsigned grid, cudaStream_t s) {
+  return p.is_bf16 ? launch_attn64_inst<HAS_BIAS, true, HD>(p, grid, s) : launch_attn64_inst<HAS_BIAS, false, HD>(p, grid, s);
+}
+
+// DPT_ATTN_V1=1 selects the first-generation kernel (attn_tc.cuh: 128-column kv steps, two CTAs per SM) - an A/B switch
+// for tools/ and the ncu before/after captures; same results within the 16-bit rounding of P.
+bool attn_v1_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_ATTN_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 // qkv [B, N, 3F] with F = heads * hd (hd = 64 or 32); bias (optional): [wmod, heads, N, ldb] 16-bit, ldb % 128 == 0
@@ -568,12 +607,13 @@ bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, int
   if (bias != nullptr && (ldb % ATT_BN != 0 || ldb < N)) return c.fail("attention: bias row stride must be a multiple of 128");
   if (c.dry) return true;  // (workspace sizing pass: buffers are null)
   if (hd == 32 && bias == nullptr) return c.fail("attention: the head_dim 32 kernel is built with bias only (SwinV2)");
+  const bool v1 = attn_v1_enabled();
   AttnParams p;
   memset(&p, 0, sizeof p);
   const int F = heads * hd;
   uint64_t dims[3] = {(uint64_t)3 * F, (uint64_t)N, (uint64_t)B};
   uint64_t str[2] = {(uint64_t)3 * F * 2, (uint64_t)3 * F * 2 * N};
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[3] = {64, v1 ? 128u : (uint32_t)A2_BN, 1};
   if (!make_tmap(&p.tmQKV, qkv, 3, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
   p.N = N; p.H = heads; p.B = B; p.F = F;
   p.is_bf16 = c.is_bf16;
@@ -582,13 +622,21 @@ bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, int
   p.bias = bias;
   p.ldb = ldb;
   p.bias_wmod = wmod > 0 ? wmod : 1;
-  dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
   const bool has_bias = bias != nullptr;
-  c.add("attn:" + c.scope, 4.0 * B * heads * (double)N * N * hd, 4.0 * (double)B * N * F * 2.0,
-        [p, grid, has_bias, hd](cudaStream_t s) {
-          if (hd == 32) return launch_attn<true, 32>(p, grid, s);
-          return has_bias ? launch_attn<true, 64>(p, grid, s) : launch_attn<false, 64>(p, grid, s);
-        });
+  const double flops = 4.0 * B * heads * (double)N * N * hd, bytes = 4.0 * (double)B * N * F * 2.0;
+  if (v1) {
+    dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
+    c.add("attn_v1:" + c.scope, flops, bytes, [p, grid, has_bias, hd](cudaStream_t s) {
+      if (hd == 32) return launch_attn<true, 32>(p, grid, s);
+      return has_bias ? launch_attn<true, 64>(p, grid, s) : launch_attn<false, 64>(p, grid, s);
+    });
+    return true;
+  }
+  const unsigned grid = (unsigned)((N + A2_BM - 1) / A2_BM) * heads * B;
+  c.add("attn:" + c.scope, flops, bytes, [p, grid, has_bias, hd](cudaStream_t s) {
+    if (hd == 32) return launch_attn64<true, 32>(p, grid, s);
+    return has_bias ? launch_attn64<true, 64>(p, grid, s) : launch_attn64<false, 64>(p, grid, s);
+  });
   return true;
 }
 
@@ -1501,6 +1549,8 @@ int run_launches(dpt_model_s* m, std::vector<LaunchFn>& launches, cudaStream_t s
 template <typename BuildFn>
 int build_and_run(dpt_model_s* h, void* ws, size_t ws_bytes, void* stream, BuildFn&& fn) {
   if (!h) return DPT_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (guard.err != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err); return DPT_ERR_CUDA; }
   std::vector<LaunchFn> launches;
   Ctx c = make_ctx(h, ws, ws_bytes, &launches, false);
   if (!fn(c)) {
@@ -1522,7 +1572,8 @@ int build_and_run(dpt_model_s* h, void* ws, size_t ws_bytes, void* stream, Build
 
 extern "C" {
 
-const char* dpt_version(void) { return "dpt_b200 0.1 (sm_100a)"; }
+const char* dpt_version(void) { return "dpt_b200 0.2 (sm_100a)"; }
+int dpt_config_size(void) { return (int)sizeof(dpt_config); }
 
 int dpt_create(const dpt_config* cfg, dpt_handle* out) {
   if (!cfg || !out) { g_err = "null argument"; return DPT_ERR_INVALID; }
@@ -1619,6 +1670,8 @@ int dpt_workspace_bytes(dpt_handle h, int B, int H, int W, size_t* bytes) {
 int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_bytes, int B, int H, int W,
                 void* stream) {
   if (!h || !img || !depth || !ws) return DPT_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (guard.err != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err); return DPT_ERR_CUDA; }
   Plan& pl = h->fwd_plan;
   if (!(pl.valid && pl.img == img && pl.out == depth && pl.ws == ws && pl.B == B && pl.H == H && pl.W == W)) {
     pl.valid = false;
@@ -1641,6 +1694,8 @@ int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_
 int dpt_forward_host(dpt_handle h, const void* host_img, void* host_depth, void* dev_img, void* dev_depth, void* ws,
                      size_t ws_bytes, int B, int H, int W, void* stream) {
   if (!h || !host_img || !host_depth || !dev_img || !dev_depth) return DPT_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (guard.err != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err); return DPT_ERR_CUDA; }
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemcpyAsync(dev_img, host_img, (size_t)B * 3 * H * W * 2, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) { h->err = std::string("H2D copy: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }

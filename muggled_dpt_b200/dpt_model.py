@@ -135,6 +135,8 @@ class DPTModel(torch.nn.Module):
         device = kwargs.get("device", None)
         dtype = kwargs.get("dtype", None)
         for a in args:
+            if isinstance(a, bool):  # positional non_blocking (bool is an int: not a device index)
+                continue
             if isinstance(a, torch.dtype):
                 dtype = a
             elif isinstance(a, (str, torch.device, int)):
@@ -252,7 +254,8 @@ class DPTModel(torch.nn.Module):
         key = (B, H, W)
         if self._ws_key != key:
             need = C.c_size_t()
-            N.check(N.lib().dpt_workspace_bytes(self._handle, B, H, W, C.byref(need)), self._handle, "dpt_workspace_bytes")
+            with torch.cuda.device(self._device):
+                N.check(N.lib().dpt_workspace_bytes(self._handle, B, H, W, C.byref(need)), self._handle, "dpt_workspace_bytes")
             self._workspace = None
             self._workspace = torch.empty(int(need.value), dtype=torch.uint8, device=self._device)
             self._ws_key = key
@@ -266,15 +269,17 @@ class DPTModel(torch.nn.Module):
             raise RuntimeError(f"Device mismatch! Image: {x.device}, model: {device}")
         if x.dtype != dtype:
             raise RuntimeError(f"Data type mismatch! Image: {x.dtype}, model: {dtype}")
-        p = self.config["patch_size_px"]
         B, _, H, W = x.shape
-        mult = (8 if self.model_type == "swinv2" else 2) * p
+        self._check_size(H, W)
+        return B, H, W
+
+    def _check_size(self, H: int, W: int):
+        mult = (8 if self.model_type == "swinv2" else 2) * self.config["patch_size_px"]
         if H % mult or W % mult:
             raise ValueError(
                 f"image size {H}x{W} is not usable: height and width must be multiples of {mult} "
                 "(the reference fails inside fusion otherwise)"
             )
-        return B, H, W
 
     # ------------------------------------------------------------------------------------------------- forward
 
@@ -306,8 +311,20 @@ class DPTModel(torch.nn.Module):
 
     def forward_host(self, host_img: torch.Tensor, host_out: torch.Tensor) -> torch.Tensor:
         """Host buffers in/out through dpt_forward_host (H2D + forward + D2H + sync)."""
-        self._require_ready()
+        device, dtype = self._require_ready()
+        for name, t in (("host_img", host_img), ("host_out", host_out)):
+            if not isinstance(t, torch.Tensor) or t.device.type != "cpu":
+                raise ValueError(f"forward_host: {name} must be a CPU tensor (pinned for full copy speed)")
+            if t.dtype != dtype:
+                raise RuntimeError(f"Data type mismatch! {name}: {t.dtype}, model: {dtype}")
+            if not t.is_contiguous():
+                raise ValueError(f"forward_host: {name} must be contiguous")
+        if host_img.dim() != 4 or host_img.shape[1] != 3:
+            raise ValueError("expected an image tensor of shape Bx3xHxW")
         B, _, H, W = host_img.shape
+        self._check_size(H, W)
+        if tuple(host_out.shape) != (B, H, W):
+            raise ValueError(f"forward_host: host_out must have shape {(B, H, W)}, got {tuple(host_out.shape)}")
         io = self._io.get((B, H, W))
         if io is None:
             io = (
@@ -381,8 +398,9 @@ class DPTModel(torch.nn.Module):
         img = image_bchw.contiguous()
         tokens = torch.empty((B, gh * gw, F), dtype=self._dtype, device=self._device)
         ws = self._get_workspace(B, H, W)
-        rc = N.lib().dpt_patch_embed(self._handle, C.c_void_p(img.data_ptr()), C.c_void_p(tokens.data_ptr()),
-                                     C.c_void_p(ws.data_ptr()), ws.numel(), B, H, W, self._stream())
+        with torch.cuda.device(self._device):
+            rc = N.lib().dpt_patch_embed(self._handle, C.c_void_p(img.data_ptr()), C.c_void_p(tokens.data_ptr()),
+                                         C.c_void_p(ws.data_ptr()), ws.numel(), B, H, W, self._stream())
         N.check(rc, self._handle, "dpt_patch_embed")
         return tokens, (gh, gw)
 
@@ -396,8 +414,9 @@ class DPTModel(torch.nn.Module):
         else:
             taps = [torch.empty((B, Np + 1, F), dtype=self._dtype, device=self._device) for _ in range(4)]
         ws = self._stage_ws(B, gh, gw)
-        rc = N.lib().dpt_encoder(self._handle, C.c_void_p(tok.data_ptr()), C.byref(N.ptr4(taps)),
-                                 C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        with torch.cuda.device(self._device):
+            rc = N.lib().dpt_encoder(self._handle, C.c_void_p(tok.data_ptr()), C.byref(N.ptr4(taps)),
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
         N.check(rc, self._handle, "dpt_encoder")
         return tuple(taps)
 
@@ -418,8 +437,9 @@ class DPTModel(torch.nn.Module):
         sizes = [((gh * k0) >> k, (gw * k0) >> k) for k in range(4)]
         maps = [self._nhwc_empty(B, Cc, h, w) for h, w in sizes]
         ws = self._stage_ws(B, gh, gw)
-        rc = N.lib().dpt_reassemble(self._handle, C.byref(N.ptr4(taps)), C.byref(N.ptr4(maps)),
-                                    C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        with torch.cuda.device(self._device):
+            rc = N.lib().dpt_reassemble(self._handle, C.byref(N.ptr4(taps)), C.byref(N.ptr4(maps)),
+                                        C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
         N.check(rc, self._handle, "dpt_reassemble")
         return tuple(maps)
 
@@ -430,8 +450,9 @@ class DPTModel(torch.nn.Module):
         gh, gw = h0 // k0, w0 // k0
         fused = self._nhwc_empty(B, Cc, h0 * 2, w0 * 2)
         ws = self._stage_ws(B, gh, gw)
-        rc = N.lib().dpt_fusion(self._handle, C.byref(N.ptr4(maps)), C.c_void_p(fused.data_ptr()),
-                                C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        with torch.cuda.device(self._device):
+            rc = N.lib().dpt_fusion(self._handle, C.byref(N.ptr4(maps)), C.c_void_p(fused.data_ptr()),
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
         N.check(rc, self._handle, "dpt_fusion")
         return fused
 
@@ -443,7 +464,8 @@ class DPTModel(torch.nn.Module):
         p = self.config["patch_size_px"]
         depth = torch.empty((B, gh * p, gw * p), dtype=self._dtype, device=self._device)
         ws = self._stage_ws(B, gh, gw)
-        rc = N.lib().dpt_head(self._handle, C.c_void_p(x.data_ptr()), C.c_void_p(depth.data_ptr()),
-                              C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        with torch.cuda.device(self._device):
+            rc = N.lib().dpt_head(self._handle, C.c_void_p(x.data_ptr()), C.c_void_p(depth.data_ptr()),
+                                  C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
         N.check(rc, self._handle, "dpt_head")
         return depth

@@ -142,11 +142,64 @@ def pack_patch_embed(w: torch.Tensor) -> torch.Tensor:
     return pack_linear(w.reshape(w.shape[0], -1))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# strict loading: unexpected keys
+#
+# The reference converts a checkpoint key by key; keys that match none of its patterns never reach
+# `load_state_dict` and are silently ignored, keys on its drop list return None, and every other converted key must
+# exist in the module tree or `load_state_dict(strict=True)` raises "Unexpected key(s)". The packers below read the
+# checkpoint through `_Tracked`, so a key under one of the reference's converted prefixes that no packer consumed is
+# reported the same way (v2_depthanything/state_dict_conversion/convert_original_state_dict_keys.py:42-70,
+# v31_beit/.../convert_midas_state_dict_keys.py:103-325, v31_swinv2/.../convert_midas_state_dict_keys.py:104-349).
+
+
+class _Tracked:
+    def __init__(self, sd: dict):
+        self.sd = sd
+        self.used = set()
+
+    def __contains__(self, key):
+        return key in self.sd
+
+    def __getitem__(self, key):
+        self.used.add(key)
+        return self.sd[key]
+
+    def unexpected(self, converted: tuple, dropped: tuple) -> list:
+        out = []
+        for k in self.sd:
+            k = str(k)
+            if k in self.used or not any(re.match(c, k) for c in converted) or any(re.search(d, k) for d in dropped):
+                continue
+            out.append(k)
+        return out
+
+
+def _raise_unexpected(keys: list):
+    if keys:
+        raise RuntimeError("Error(s) in loading state_dict: Unexpected key(s): " + ", ".join(keys[:8]) +
+                           (" ..." if len(keys) > 8 else ""))
+
+
+_DAV2_CONVERTED = (r"pretrained\.patch_embed", r"pretrained\.cls_token$", r"pretrained\.pos_embed$", r"pretrained\.norm",
+                   r"pretrained\.blocks\.\d+", r"depth_head\.projects", r"depth_head\.resize_layers",
+                   r"depth_head\.scratch\.layer\d+_rn", r"depth_head\.scratch\.refinenet", r"depth_head\.scratch\.output_conv")
+_DAV2_DROPPED = (r"^depth_head\.scratch\.refinenet4\.resConfUnit1",)
+_BEIT_CONVERTED = (r"pretrained\.model\.patch_embed", r"pretrained\.model\.cls_token$", r"pretrained\.model\.blocks\.\d+",
+                   r"pretrained\.act_postprocess", r"scratch\.layer\d+_rn", r"scratch\.refinenet", r"scratch\.output_conv")
+_BEIT_DROPPED = (r"relative_position_index", r"^scratch\.refinenet4\.resConfUnit1")
+_SWIN_CONVERTED = (r"pretrained\.model\.patch_embed\.", r"pretrained\.model\.layers\.\d+\.blocks\.\d+",
+                   r"pretrained\.model\.layers\.\d+\.downsample", r"pretrained\.act_postprocess", r"scratch\.layer\d+_rn",
+                   r"scratch\.refinenet", r"scratch\.output_conv")
+_SWIN_DROPPED = (r"attn_mask", r"^scratch\.refinenet4\.resConfUnit1")
+
+
 def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
     """Returns {packed name: (fp32 cpu tensor, kind)} with kind in {"half", "half_colsum", "f32", "host"}."""
     F = cfg["features_per_token"]
     L = cfg["num_blocks"]
     missing = []
+    sd = _Tracked(sd)
 
     def get(key, default_shape=None, fill=0.0):
         if key in sd:
@@ -246,6 +299,8 @@ def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
     if missing and strict:
         raise RuntimeError("Error(s) in loading state_dict: Missing key(s): " + ", ".join(missing[:8]) +
                            (" ..." if len(missing) > 8 else ""))
+    if strict:
+        _raise_unexpected(sd.unexpected(_DAV2_CONVERTED, _DAV2_DROPPED))
     return out
 
 
@@ -286,6 +341,7 @@ def pack_beit(sd: dict, cfg: dict, strict: bool = True) -> dict:
     F = cfg["features_per_token"]
     L = cfg["num_blocks"]
     missing = []
+    sd = _Tracked(sd)
 
     def get(key):
         if key in sd:
@@ -378,6 +434,8 @@ def pack_beit(sd: dict, cfg: dict, strict: bool = True) -> dict:
             raise RuntimeError("Error(s) in loading state_dict: Missing key(s): " + ", ".join(missing[:8]) +
                                (" ..." if len(missing) > 8 else ""))
         raise RuntimeError("non-strict loading of BEiT checkpoints with missing keys is not supported: " + missing[0])
+    if strict:
+        _raise_unexpected(sd.unexpected(_BEIT_CONVERTED, _BEIT_DROPPED))
     return out
 
 
@@ -429,6 +487,7 @@ def pack_swinv2(sd: dict, cfg: dict, strict: bool = True) -> dict:
     tensors are dropped (:179-181), `logit_scale` is clamped at ln(100) and exponentiated once (:115-131), q/v biases
     become the bias of the fused QKV GEMM."""
     missing = []
+    sd = _Tracked(sd)
 
     def get(key):
         if key in sd:
@@ -505,4 +564,6 @@ def pack_swinv2(sd: dict, cfg: dict, strict: bool = True) -> dict:
     if missing:
         raise RuntimeError("Error(s) in loading state_dict: Missing key(s): " + ", ".join(missing[:8]) +
                            (" ..." if len(missing) > 8 else ""))
+    if strict:
+        _raise_unexpected(sd.unexpected(_SWIN_CONVERTED, _SWIN_DROPPED))
     return out

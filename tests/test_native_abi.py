@@ -35,8 +35,17 @@ def test_version_and_error_strings_without_gpu():
 def test_config_struct_layout_matches_header():
     from muggled_dpt_b200 import _native as N
 
-    # 14 ints + 1 float + 14 ints (SwinV2 block) + taps_last4 + mlp_swiglu, no padding
-    assert ctypes.sizeof(N.DptConfig) == 31 * 4
+    # the struct the library was compiled with (include/dpt_b200.h) == the ctypes mirror, field for field
+    assert ctypes.sizeof(N.DptConfig) == N.lib().dpt_config_size()
+    header = open(os.path.join(ROOT, "include", "dpt_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header[header.index("typedef struct dpt_config"):header.index("} dpt_config;")], flags=re.S)
+    declared = re.findall(r"\b(?:int|float)\s+([^;]+);", body)
+    names = [n.split("[")[0].strip() for d in declared for n in d.split(",")]
+    assert names == [f[0] for f in N.DptConfig._fields_]
+    # the binding sketch a maintainer would copy from INTEGRATION.md carries the same fields
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sketch = doc[doc.index("class _Cfg(C.Structure)"):doc.index("_lib.dpt_create.argtypes")]
+    assert re.findall(r'\("([a-z0-9_]+)", C\.c_', sketch) == names
 
 
 def test_allgather_entry_rejects_bad_arguments_without_gpu():

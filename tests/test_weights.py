@@ -97,6 +97,42 @@ def test_dropped_and_missing_keys():
     Wt.pack_depthanything_v2(sd2, cfg, strict=False)
 
 
+def test_unexpected_keys_follow_the_reference_converter():
+    """strict loading: a stray key under a prefix the reference's converter renames is an "Unexpected key(s)" error (it
+    would reach load_state_dict(strict=True)); a key the converter ignores, or one on its drop list, is not."""
+    sd = O.make_synthetic_state_dict("tiny", seed=3, base_grid=5)
+    cfg = Wt.get_model_config_from_state_dict(sd, False, True)
+    ignored = dict(sd, **{"something.else": torch.zeros(1), "pretrained.mask_token": torch.zeros(1, 1, 4),
+                          "depth_head.scratch.refinenet4.resConfUnit1.conv1.bias": torch.zeros(4)})
+    Wt.pack_depthanything_v2(ignored, cfg, strict=True)
+    stray = dict(sd, **{"pretrained.blocks.1.attn.extra.weight": torch.zeros(2)})
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        Wt.pack_depthanything_v2(stray, cfg, strict=True)
+    Wt.pack_depthanything_v2(stray, cfg, strict=False)
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):  # the live reference agrees (build container only)
+        import sys
+
+        sys.path.insert(0, ref_root)
+        try:
+            from muggled_dpt.make_depthanythingv2_dpt import make_depthanythingv2_dpt_from_original_state_dict as mk
+        finally:
+            sys.path.remove(ref_root)
+        mk(dict(ignored), False, True, True)
+        with pytest.raises(RuntimeError, match="Unexpected key"):
+            mk(dict(stray), False, True, True)
+    bsd = O.make_synthetic_state_dict_beit("beit_tiny", seed=1)
+    bcfg = Wt.get_model_config_from_midas_beit_state_dict(bsd, False, True)
+    Wt.pack_beit(dict(bsd, **{"pretrained.model.blocks.0.attn.relative_position_index": torch.zeros(3)}), bcfg)
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        Wt.pack_beit(dict(bsd, **{"scratch.output_conv.9.weight": torch.zeros(3)}), bcfg)
+    ssd = O.make_synthetic_state_dict_swinv2("swinv2_micro", seed=1)
+    scfg = Wt.get_model_config_from_midas_swinv2_state_dict(ssd, False, True)
+    Wt.pack_swinv2(ssd, scfg)  # carries attn_mask keys (dropped)
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        Wt.pack_swinv2(dict(ssd, **{"pretrained.model.layers.0.blocks.0.attn.stray": torch.zeros(3)}), scfg)
+
+
 def test_model_type_sniffing():
     f = Wt.determine_model_type_from_state_dict
     assert f("x.pth", {"pretrained.model.layers.0.blocks.0.attn.logit_scale": 0}) == "swinv2"

@@ -1,8 +1,14 @@
 #!/usr/bin/env python3
-"""Per-stage parity of the CUDA path against the fp32 CPU oracle at the benchmark's image size (504x504, B=1) for the
-Depth-Anything-V2 ViT-S / ViT-B / ViT-L architectures (synthetic seeded checkpoints), in bf16 and fp16: relative L2,
-max-abs and max-abs / max|ref| per stage (stages run end to end, so errors compound as they do in a real forward).
-Writes one JSON document. usage (GPU box): python tools/parity_report.py [out.json] [models...]"""
+"""Per-stage parity of the CUDA path against the fp32 CPU oracle on the five BASELINE.json configurations at their real
+architectures and image sizes (batch reduced so the CPU oracle finishes in seconds; frames of a batch never interact):
+
+  S  Depth-Anything-V2 ViT-S  1x3x504x504  bf16 + fp16        B  ViT-B  2x3x504x504  bf16 + fp16
+  L  ViT-L  1x3x504x504  bf16 + fp16                          W  SwinV2-L  1x3x384x384  fp16 (+ bf16)
+  E  BEiT-L  1x3x384x384  bf16 (+ fp16)
+
+Stages run end to end (errors compound as in a real forward). Per stage: relative L2, max-abs, max-abs / max|ref|
+("max_rel", the north star's wording applied to a map whose small values sit next to a ReLU). Writes one JSON document.
+usage (GPU box): python tools/parity_report.py [out.json] [config letters, default SBLWE]"""
 import json
 import os
 import sys
@@ -16,7 +22,12 @@ from muggled_dpt_b200 import make_dpt_from_state_dict  # noqa: E402
 from oracle import dpt_oracle as O  # noqa: E402  (the checker)
 
 out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "parity_report.json")
-models = sys.argv[2:] or ["vits", "vitb", "vitl"]
+which = sys.argv[2] if len(sys.argv) > 2 else "SBLWE"
+
+CONFIGS = {
+    "S": ("vits", 1, 504, "dav2"), "B": ("vitb", 2, 504, "dav2"), "L": ("vitl", 1, 504, "dav2"),
+    "W": ("swinv2_large_384", 1, 384, "swin"), "E": ("beit_large_384", 1, 384, "beit"),
+}
 
 
 def err(a, b):
@@ -27,12 +38,18 @@ def err(a, b):
 
 
 report = {}
-for name in models:
-    sd = O.make_synthetic_state_dict(name, seed=11)
-    img = O.make_input(1, 504, 504, seed=2)
-    ref = O.forward(sd, img, return_stages=True)
+for key in which:
+    name, B, S, fam = CONFIGS[key]
+    if fam == "dav2":
+        sd, fwd, fname = O.make_synthetic_state_dict(name, seed=11), O.forward, f"depth_anything_v2_{name}.pth"
+    elif fam == "beit":
+        sd, fwd, fname = O.make_synthetic_state_dict_beit(name, seed=11), O.forward_beit, f"dpt_{name}.pt"
+    else:
+        sd, fwd, fname = O.make_synthetic_state_dict_swinv2(name, seed=11), O.forward_swinv2, f"dpt_{name}.pt"
+    img = O.make_input(B, S, S, seed=2)
+    ref = fwd(sd, img, return_stages=True)
     with tempfile.TemporaryDirectory() as td:
-        path = os.path.join(td, f"depth_anything_v2_{name}.pth")
+        path = os.path.join(td, fname)
         torch.save(sd, path)
         _, model = make_dpt_from_state_dict(path)
     for dtype in (torch.bfloat16, torch.float16):
@@ -53,9 +70,11 @@ for name in models:
             r[f"map{i}"] = err(maps[i], ref["maps"][i])
         r["fused"] = err(fused, ref["fused"])
         r["depth"] = err(depth, ref["depth"])
-        report[f"{name}_{str(dtype).split('.')[-1]}"] = r
-        print(name, dtype, "depth rel_l2 %.2e max_abs %.2e max_rel %.2e | worst stage rel_l2 %.2e" % (
+        report[f"{key}:{name}_B{B}_{S}_{str(dtype).split('.')[-1]}"] = r
+        print(key, name, dtype, "depth rel_l2 %.2e max_abs %.2e max_rel %.2e | worst stage rel_l2 %.2e" % (
             r["depth"]["rel_l2"], r["depth"]["max_abs"], r["depth"]["max_rel"], max(v["rel_l2"] for v in r.values())), flush=True)
+    del model, ref, sd
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
-json.dump({"image": "1x3x504x504 N(0,1), seed 2", "reference": "oracle/dpt_oracle.py fp32 CPU (bit-exact to the reference on the golden fixtures)",
+json.dump({"image": "N(0,1) inputs, seed 2; synthetic seeded checkpoints, seed 11",
+           "reference": "oracle/dpt_oracle.py fp32 CPU (bit-exact to the reference on the golden fixtures)",
            "stages": report}, open(out_path, "w"), indent=1)
