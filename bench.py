@@ -2,7 +2,7 @@
 """
 bench.py - depth frames/s of the DPT hot path (DPTModel.forward) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--model vitl|vitb|vits]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference|reference-gpu] [--model vitl|vitb|vits]
                   [--batch B] [--size S] [--dtype bf16|fp16] [--scaling strong|weak]
 
 Workload (BASELINE.json metric "depth frames/sec at 518^2 ViT-L bf16, 1/2/4/8xB200", configs[2]): Depth-Anything-V2
@@ -14,7 +14,13 @@ kernels on its frames and the depth maps are all-gathered once per step over NCC
 Printed JSON line (rank 0): value = frames/s with inputs resident in HBM (CUDA events, max over ranks);
 e2e = same metric through the host-buffer C-ABI call (dpt_forward_host: pinned host -> H2D -> forward -> D2H);
 roofline = the dominant kernel (tcgen05 GEMM) from per-launch CUDA events recorded inside the library during extra
-profiled steps; cpu_baseline = the oracle's fp32 CPU restatement of the reference path on this box's host cores.
+profiled steps; cpu_baseline = the reference's fp32 CPU path on this box's host cores.
+
+Reference arms (no product code on their path): `--impl reference` = the UNMODIFIED reference package from oracle/_ref
+(placed there by oracle/build_ref.py; the oracle port stands in only when that copy is absent) through its own
+make_dpt_from_state_dict() / DPTModel.forward() on the host CPU in fp32, W warm-up and K timed steps like the native
+arm, each step a bounded sample (one frame) of the batch; `--impl reference-gpu` = the same reference model moved to
+the B200 with stock PyTorch eager (`model.to("cuda", bf16, channels_last)`, SURVEY.md section 8d "the real bar").
 """
 import argparse
 import json
@@ -38,7 +44,8 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-gpu"])
+    ap.add_argument("--ref-frames-per-step", type=int, default=1, help="reference arm: frames per timed step (bounded sample)")
     ap.add_argument("--model", default="vitl",
                     choices=["vitl", "vitb", "vits", "tiny", "beit_large_384", "beit_base_384", "beit_tiny",
                              "swinv2_large_384", "swinv2_base_384", "swinv2_tiny_256", "swinv2_micro"])
@@ -147,30 +154,65 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def time_cpu_oracle(model_name, size, frames, threads=None):
-    """fp32 CPU restatement of the reference path (oracle/), B=1 per step: returns (frames/s, cores, sample text)"""
+def workload_text(model_name, batch, size, dtype):
+    fam = "MiDaS v3.1" if model_name.startswith(("beit", "swinv2")) else "Depth-Anything-V2"
+    return (f"{fam} {model_name} (synthetic seeded weights), global batch {batch}, 3x{size}x{size}"
+            + (" (reference's effective 518 setting)" if size == 504 else "") + f", {dtype}")
+
+
+def workload_config(model_name, b_global, b_local, world, size, dtype):
+    """the `config` object of the JSON line - identical for the native and the reference arms (it names the workload)"""
+    return {"workload": workload_text(model_name, b_global, size, dtype), "global_batch": b_global,
+            "per_gpu_batch": b_local, "parallelism": f"dp{world} batch-shard + all-gather",
+            "l2": "256 MiB buffer rewritten between iterations (L2 flush); per-step working set >> 126 MB L2"}
+
+
+def load_reference_model(model_name):
+    """(model, kind): the unmodified reference from oracle/_ref through its own factory, else the oracle port"""
+    import torch
+
+    from oracle import dpt_oracle as O
+    from oracle.build_ref import import_reference, ref_available
+
+    sd, fwd = _oracle_model(O, model_name)
+    if not ref_available():
+        return (lambda x: fwd(sd, x)), "port", None
+    make_dpt = import_reference()
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, _checkpoint_file_name(model_name))
+        torch.save(sd, path)
+        del sd
+        _, model = make_dpt.make_dpt_from_state_dict(path)
+    return model, "reference", model
+
+
+def time_cpu_reference(model_name, size, frames, threads=None):
+    """the reference's fp32 CPU path, B=1 per step: returns (frames/s, cores, sample text, kind)"""
     import torch
 
     from oracle import dpt_oracle as O
 
     torch.set_num_threads(threads or host_threads())
     cores = torch.get_num_threads()
-    sd, fwd = _oracle_model(O, model_name)
+    fwd, kind, _ = load_reference_model(model_name)
     img = O.make_input(1, size, size, seed=2)
-    fwd(sd, img)  # warm-up
-    ts = []
-    for _ in range(frames):
-        t0 = time.perf_counter()
-        fwd(sd, img)
-        ts.append(time.perf_counter() - t0)
+    with torch.inference_mode():
+        fwd(img)  # warm-up
+        ts = []
+        for _ in range(frames):
+            t0 = time.perf_counter()
+            fwd(img)
+            ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
-    sample = f"{frames} frames of B=1 {model_name} {size}x{size} fp32 after 1 warm-up, median; torch threads={cores} of {os.cpu_count()} cpus"
-    return 1.0 / med, cores, sample
+    what = "unmodified reference (oracle/_ref) DPTModel.forward" if kind == "reference" else "oracle port of the reference path"
+    sample = (f"{what}: {frames} frames of B=1 {model_name} {size}x{size} fp32 after 1 warm-up, median; "
+              f"torch threads={cores} of {os.cpu_count()} cpus")
+    return 1.0 / med, cores, sample, kind
 
 
 def run_reference(args, rank, world):
-    """reference arm: the reference's own CPU implementation of the path == the oracle port (the reference is pure
-    Python/PyTorch and /root/reference does not exist on the GPU box), all host threads, bounded sample per step."""
+    """reference arm on the host CPU: the reference's own implementation of the path (oracle/_ref), all host threads,
+    the same warm-up / step counts as the native arm, each step a bounded sample of the workload."""
     if rank != 0:
         return
     import torch
@@ -179,28 +221,81 @@ def run_reference(args, rank, world):
 
     torch.set_num_threads(host_threads())
     cores = torch.get_num_threads()
-    sd, fwd = _oracle_model(O, args.model)
-    img = O.make_input(1, args.size, args.size, seed=2)
-    for _ in range(max(1, min(args.warmup, 1))):
-        fwd(sd, img)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fwd(sd, img)
-    dt = time.perf_counter() - t0
-    fps = steps / dt
-    sample = (f"each step = 1 frame (a bounded sample of the batch-{args.batch} workload) of {args.model} "
-              f"{args.size}x{args.size}, fp32 CPU, {steps} timed steps; torch threads={cores} of {os.cpu_count()} cpus")
+    fwd, kind, _ = load_reference_model(args.model)
+    n = max(1, args.ref_frames_per_step)
+    img = O.make_input(n, args.size, args.size, seed=2)
+    warmup, steps = max(args.warmup, 0), max(args.steps, 1)
+    with torch.inference_mode():
+        for _ in range(warmup):
+            fwd(img)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fwd(img)
+        dt = time.perf_counter() - t0
+    fps = n * steps / dt
+    b_local = args.batch // world if args.scaling == "strong" else args.batch
+    b_global = args.batch if args.scaling == "strong" else args.batch * world
+    what = "unmodified reference (oracle/_ref) make_dpt_from_state_dict -> DPTModel.forward" if kind == "reference" \
+        else "oracle port of the reference path (oracle/_ref absent)"
+    sample = (f"{what}; each step = {n} frame(s), a bounded sample of the batch-{b_global} workload, {args.model} "
+              f"{args.size}x{args.size}, fp32 on the host CPU, {warmup} warm-up + {steps} timed steps; "
+              f"torch threads={cores} of {os.cpu_count()} cpus")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": args.scaling,
+        "warmup": warmup, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"MiDaS v3.1 {args.model}" if args.model.startswith(("beit", "swinv2")) else f"Depth-Anything-V2 {args.model}")
-                               + f" (synthetic seeded weights), global batch {args.batch}, 3x{args.size}x{args.size}"
-                               + (" (reference's effective 518 setting)" if args.size == 504 else "") + ", fp32 on the host CPU",
-                   "global_batch": args.batch, "parallelism": "host cpu"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.model, b_global, b_local, world, args.size, args.dtype),
+        "reference_run": {"device": "host cpu", "compute_dtype": "f32", "frames_per_step": n, "kind": kind},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(args, rank, world):
+    """the on-box bar: the unmodified reference on the same B200 through stock PyTorch eager,
+    model.to("cuda", bf16 / fp16, channels_last) as run_image.py:158 does, same batch / size / dtype as the native arm."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import dpt_oracle as O
+
+    assert torch.cuda.is_available()
+    fwd, kind, model = load_reference_model(args.model)
+    if model is None:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref is absent (run oracle/build_ref.py where /root/reference exists)"}))
+        return
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    dev = torch.device("cuda", 0)
+    model.to(device=dev, dtype=dtype, memory_format=torch.channels_last)
+    B, S = args.batch, args.size
+    g = torch.Generator().manual_seed(1234)
+    img = torch.randn(B, 3, S, S, generator=g).to(dtype).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(0)
+    with torch.inference_mode():
+        for _ in range(max(args.warmup, 3)):
+            flush.zero_()
+            model(img)
+        torch.cuda.synchronize()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            flush.zero_()
+            out = model(img)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    line = {
+        "impl": "reference-gpu", "metric": METRIC, "value": B * args.steps / (ms / 1000.0), "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args.model, B, B, 1, S, args.dtype), "clocks": clocks,
+        "reference_run": {"device": "cuda:0 (stock PyTorch eager: cuBLAS / cuDNN / fused SDPA)", "compute_dtype": args.dtype,
+                          "memory_format": "channels_last", "kind": kind, "output_shape": list(out.shape)},
     }
     print(json.dumps(line), flush=True)
 
@@ -213,6 +308,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu(args, rank, world)
         return
 
     import torch
@@ -370,8 +468,8 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on this box's host cores
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = time_cpu_oracle(args.model, S, args.cpu_baseline_frames)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        v, cores, sample, kind = time_cpu_reference(args.model, S, args.cpu_baseline_frames)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
     if rank == 0:
         gf = algorithmic_gflop_per_frame(args.model, S)
@@ -380,13 +478,9 @@ def main():
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {
-                "workload": (f"MiDaS v3.1 {args.model}" if args.model.startswith(("beit", "swinv2")) else f"Depth-Anything-V2 {args.model}")
-                            + f" (synthetic seeded weights), global batch {b_global}, 3x{S}x{S}"
-                            + (" (reference's effective 518 setting)" if S == 504 else "") + f", {args.dtype}",
-                "global_batch": b_global, "per_gpu_batch": b_local, "parallelism": f"dp{world} batch-shard + all-gather",
-                "l2": "256 MiB buffer rewritten between iterations (L2 flush); per-step working set >> 126 MB L2",
-            },
+            "config": workload_config(args.model, b_global, b_local, world, S, args.dtype),
+            "value_path": "DPTModel.forward_into on caller-owned device buffers (model(x) adds one input copy_ and one "
+                          "output clone, ~65 MB of device copies at B=32)",
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,

@@ -122,6 +122,20 @@ int dpt_reassemble(dpt_handle h, const void* const taps[4], void* const maps[4],
 /* FusionModel.forward (fusion_model.py:55-80): maps -> fused [B, 8gh, 8gw, C] */
 int dpt_fusion(dpt_handle h, const void* const maps[4], void* fused, void* workspace, size_t workspace_bytes, int B,
                int gh, int gw, void* stream);
+/* One fusion block on its own (FusionBlock.forward fusion_model.py:148-154; level 3 = TopMostFusionBlock.forward
+ * :113-114, prev_fused = NULL): reasm_map, prev_fused [B, map_h, map_w, C] -> out [B, 2*map_h, 2*map_w, C]. This is
+ * what experiments/fusion_scaling.py:330-333 calls as dpt_model.fusion.blocks[i](...). Workspace: the one sized by
+ * dpt_workspace_bytes for the image this map belongs to is always large enough. */
+int dpt_fusion_block(dpt_handle h, int level, const void* reasm_map, const void* prev_fused, void* out,
+                     void* workspace, size_t workspace_bytes, int B, int map_h, int map_w, void* stream);
+/* dpt_encoder with debug capture (demo_helpers/model_capture.py:15-61 forward hooks): for encoder block i (running
+ * index over all blocks / all SwinV2 stages, i < num_blocks) probs[i], if not NULL, receives the attention
+ * probabilities softmax(scale q k^T + bias) as [B, heads, N, N] (SwinV2: [B*windows, heads, A, A]) 16-bit - what the
+ * reference's nn.Softmax module outputs (transformer_block.py:132) - and block_out[i], if not NULL, the block's output
+ * tokens [B, N, F] 16-bit (TransformerBlock.forward :53-65). Either array may be NULL. Never used by dpt_forward. */
+int dpt_encoder_capture(dpt_handle h, const void* tokens, void* const taps[4], void* const* probs,
+                        void* const* block_out, int num_blocks, void* workspace, size_t workspace_bytes, int B, int gh,
+                        int gw, void* stream);
 /* MonocularDepthHead.forward (head_model.py:89-106): fused -> depth [B, P*gh, P*gw] */
 int dpt_head(dpt_handle h, const void* fused, void* depth, void* workspace, size_t workspace_bytes, int B, int gh,
              int gw, void* stream);

@@ -66,6 +66,8 @@ SYMBOLS = [
     ("dpt_reassemble", _I, [_VP, _PP4, _PP4, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_fusion", _I, [_VP, _PP4, _VP, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_head", _I, [_VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP]),
+    ("dpt_fusion_block", _I, [_VP, _I, _VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP]),
+    ("dpt_encoder_capture", _I, [_VP, _VP, _PP4, _VP, _VP, _I, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_op_conv_gemm", _I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     ("dpt_op_attention", _I, [_VP, _VP, C.c_int64, _I, _VP, _I, _I, _I, _I, _F, _I, _VP]),
     ("dpt_op_layernorm", _I, [_VP, _VP, _VP, _VP, C.c_int64, _I, _F, _I, _VP]),

@@ -105,6 +105,12 @@ struct Ctx {
   int is_bf16;
   int num_sms;
   std::string scope;  // label prefix for launches recorded by the current stage builder
+  // debug capture (dpt_encoder_capture): per encoder block, where to dump the attention probabilities / block output
+  void* const* cap_probs = nullptr;
+  void* const* cap_block_out = nullptr;
+  int cap_blocks = 0;
+  void* cap_probs_at(int i) const { return (cap_probs && i < cap_blocks) ? cap_probs[i] : nullptr; }
+  void* cap_block_out_at(int i) const { return (cap_block_out && i < cap_blocks) ? cap_block_out[i] : nullptr; }
   bool fail(const std::string& s) {
     if (ok) err = s;
     ok = false;
@@ -640,6 +646,25 @@ bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, int
   return true;
 }
 
+// Debug only (dpt_encoder_capture): attention probabilities of one block -> probs [Bt, heads, N, N] 16-bit
+bool add_attn_probs(Ctx& c, const void* qkv, const void* bias, long long ldb, int wmod, void* probs, int Bt, int N,
+                    int heads, int hd, float scale) {
+  if (c.dry) return true;
+  const int is_bf16 = c.is_bf16;
+  const int wm = wmod > 0 ? wmod : 1;
+  c.add("attn_probs(debug):" + c.scope, 6.0 * Bt * heads * (double)N * N * hd, (double)Bt * heads * N * N * 2.0, [=](cudaStream_t s) {
+    const dim3 grid((unsigned)N, (unsigned)heads, (unsigned)Bt);
+    if (is_bf16)
+      attn_probs_kernel<__nv_bfloat16><<<grid, 128, hd * sizeof(float), s>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)bias, ldb, wm,
+                                                                          (__nv_bfloat16*)probs, N, heads, hd, scale);
+    else
+      attn_probs_kernel<__half><<<grid, 128, hd * sizeof(float), s>>>((const __half*)qkv, (const __half*)bias, ldb, wm, (__half*)probs, N,
+                                                                    heads, hd, scale);
+    return cudaGetLastError();
+  });
+  return true;
+}
+
 int ew_grid(long long n, int block, int num_sms) {
   long long g = (n + block - 1) / block;
   const long long cap = (long long)num_sms * 16;
@@ -903,8 +928,10 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
           return cudaGetLastError();
         });
       }
+      if (c.cap_probs_at(i)) add_attn_probs(c, qkv, bias_buf, ldb, 1, c.cap_probs_at(i), B, N, heads, 64, scale);
       add_attention(c, qkv, bias_buf, ldb, 1, att, B, N, heads, 64, scale);
     } else {
+      if (c.cap_probs_at(i)) add_attn_probs(c, qkv, nullptr, 0, 1, c.cap_probs_at(i), B, N, heads, 64, scale);
       add_attention(c, qkv, nullptr, 0, 1, att, B, N, heads, 64, scale);
     }
     {
@@ -942,6 +969,7 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       op.stats_out = stats; op.stats_parts = &stats_parts; op.out16 = ln;
       add_gemm(c, op);
     }
+    if (c.cap_block_out_at(i)) add_cast_to_half(c, x, c.cap_block_out_at(i), M * F, "block_out(debug)");
     // taps: last block of each quarter (DA-V2, BEiT) or the last four blocks (DA-V1, image_encoder_model.py:92-103)
     const bool is_tap = cfg.taps_last4 ? (i >= L - 4) : ((i + 1) % per_stage == 0);
     if (is_tap) {
@@ -1013,6 +1041,7 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
     });
   }
   int sgh = gh, sgw = gw;
+  int blk_index = 0;  // running block number over the four stages (debug capture)
   for (int st = 0; st < 4 && c.ok; ++st) {
     const int F = F0 << st, heads = cfg.heads_per_stage[st];
     if (heads * 32 != F) return c.fail("SwinV2 stages must have 32 features per head");
@@ -1118,6 +1147,7 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
           return cudaGetLastError();
         });
       }
+      if (c.cap_probs_at(blk_index)) add_attn_probs(c, qkv, bias, ldb, n_wm, c.cap_probs_at(blk_index), B * nW, A, heads, 32, 1.0f);
       add_attention(c, qkv, bias, ldb, n_wm, att, B * nW, A, heads, 32, 1.0f);
       {
         GemmOp op;
@@ -1163,6 +1193,8 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
           return cudaGetLastError();
         });
       }
+      if (c.cap_block_out_at(blk_index)) add_cast_to_half(c, x, c.cap_block_out_at(blk_index), M * F, "block_out(debug)");
+      ++blk_index;
     }
     c.ar.reset(mk_stage);
     c.scope = "tap" + std::to_string(st);
@@ -1325,75 +1357,86 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
 // FusionModel.forward - v2_depthanything/fusion_model.py:55-80,148-154,159-220
 // The 1x1 output projection is applied before the x2 bilinear upsample (they commute: both are linear and the
 // interpolation weights sum to one), a 4x FLOP saving - SURVEY.md §8a-bis.
+
+// One fusion block (FusionBlock.forward fusion_model.py:148-154; lvl 3 = TopMostFusionBlock :113-114):
+//   up = upsample2x(out1x1(RCU2(lvl < 3 ? RCU1(r) + f_prev : r)))      r [B,h,w,C], f_prev [B,h,w,C], up [B,2h,2w,C]
+// r_relu (optional) = relu(r) already materialised by the producer of r.
+bool build_fusion_level(Ctx& c, int lvl, const void* r, const void* r_relu, const void* f_prev, void* up, int B, int h,
+                        int w) {
+  const dpt_config& cfg = c.m->cfg;
+  const int C = cfg.fusion_channels;
+  const int hd = half_dt(c);
+  if (lvl < 0 || lvl > 3) return c.fail("fusion: level must be 0..3");
+  if (lvl < 3 && f_prev == nullptr && !c.dry) return c.fail("fusion: levels 0..2 need the previous fusion output");
+  const size_t mk = c.ar.mark();
+  const size_t big = (size_t)B * h * w * C * 2;
+  void* t_buf = c.ar.alloc(big);
+  void* t_relu = c.ar.alloc(big);
+  void* a_relu = c.ar.alloc(big);
+  void* v_buf = c.ar.alloc(big);
+  void* w_buf = c.ar.alloc(big);
+  void* r_relu_tmp = r_relu ? nullptr : c.ar.alloc(big);
+  const std::string pre = "fus" + std::to_string(lvl) + ".";
+  c.scope = pre;
+  if (!r_relu) {
+    add_relu_copy(c, r, r_relu_tmp, (long long)B * h * w * C);
+    r_relu = r_relu_tmp;
+  }
+  auto conv3 = [&](const void* in, const std::string& wn, int act, void* out, const void* add1, const void* add2,
+                   void* out_relu) {
+    const Weight *ww = get_w(c, wn + ".w", hd), *bb = get_w(c, wn + ".b", DPT_F32);
+    if (!c.ok) return;
+    GemmOp op;
+    op.A = in; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
+    op.Wt_ptr = ww->ptr; op.N = C; op.taps = 9; op.kpad = (int)ww->shape[1] / 9;
+    op.bias = (const float*)bb->ptr; op.act = act; op.out = out; op.add1 = add1; op.add2 = add2;
+    op.out2_relu = out_relu;
+    const std::string lab = wn.substr(pre.size());
+    op.label = lab.c_str();
+    add_gemm(c, op);
+  };
+  const void* t = r;
+  const void* tr = r_relu;
+  if (lvl < 3) {
+    // conv_reassembly (ResidualConv2D) + previous fusion
+    conv3(r_relu, pre + "rcu1.c1", ACT_RELU, a_relu, nullptr, nullptr, nullptr);
+    conv3(a_relu, pre + "rcu1.c2", ACT_NONE, t_buf, r, f_prev, t_relu);
+    t = t_buf;
+    tr = t_relu;
+  }
+  // scale_proj_seq: ResidualConv2D -> (1x1 projection, x2 upsample)
+  conv3(tr, pre + "rcu2.c1", ACT_RELU, a_relu, nullptr, nullptr, nullptr);
+  conv3(a_relu, pre + "rcu2.c2", ACT_NONE, v_buf, t, nullptr, nullptr);
+  {
+    const Weight *ww = get_w(c, pre + "out.w", hd), *bb = get_w(c, pre + "out.b", DPT_F32);
+    if (!c.ok) return false;
+    GemmOp op;
+    op.A = v_buf; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
+    op.Wt_ptr = ww->ptr; op.N = C; op.taps = 1; op.kpad = (int)ww->shape[1];
+    op.bias = (const float*)bb->ptr; op.out = w_buf; op.label = "out1x1";
+    add_gemm(c, op);
+  }
+  add_resize(c, w_buf, up, B, h, w, 2 * h, 2 * w, C);
+  c.ar.reset(mk);
+  return c.ok;
+}
+
 bool build_fusion(Ctx& c, const void* const maps[4], const void* const maps_relu_in[4], void* fused, int B, int h0,
                   int w0) {
   // h0 x w0 = size of the finest reassembly map (4x the patch grid for ViT/BEiT, the patch grid for SwinV2)
   const dpt_config& cfg = c.m->cfg;
   const int C = cfg.fusion_channels;
   if (h0 % 8 || w0 % 8) return c.fail("reassembly map size must be divisible by 8");
-  const int hd = half_dt(c);
   const size_t mk = c.ar.mark();
-  const int hs[4] = {h0, h0 / 2, h0 / 4, h0 / 8};
-  const int ws[4] = {w0, w0 / 2, w0 / 4, w0 / 8};
-  const void* f_prev = nullptr;  // previous fusion output, already at this level's resolution
-  void* f_bufs[2] = {nullptr, nullptr};
-  // upsampled outputs ping-pong between two buffers sized for the largest consumer (level 0 input = 4g) ; the final
+  // upsampled outputs ping-pong between two buffers sized for the largest consumer (level 0 input = 4g); the final
   // one goes to `fused`.
-  f_bufs[0] = c.ar.alloc((size_t)B * hs[0] * ws[0] * C * 2);
-  f_bufs[1] = c.ar.alloc((size_t)B * hs[0] * ws[0] * C * 2);
-  const size_t big = (size_t)B * hs[0] * ws[0] * C * 2;
-  void* t_buf = c.ar.alloc(big);
-  void* t_relu = c.ar.alloc(big);
-  void* a_relu = c.ar.alloc(big);
-  void* v_buf = c.ar.alloc(big);
-  void* w_buf = c.ar.alloc(big);
-  void* r_relu_tmp = c.ar.alloc(big);
+  void* f_bufs[2];
+  f_bufs[0] = c.ar.alloc((size_t)B * h0 * w0 * C * 2);
+  f_bufs[1] = c.ar.alloc((size_t)B * h0 * w0 * C * 2);
+  const void* f_prev = nullptr;  // previous fusion output, already at this level's resolution
   for (int lvl = 3; lvl >= 0 && c.ok; --lvl) {
-    const int h = hs[lvl], w = ws[lvl];
-    const std::string pre = "fus" + std::to_string(lvl) + ".";
-    c.scope = pre;
-    const void* r = maps[lvl];
-    const void* r_relu = maps_relu_in ? maps_relu_in[lvl] : nullptr;
-    if (!r_relu) {
-      add_relu_copy(c, r, r_relu_tmp, (long long)B * h * w * C);
-      r_relu = r_relu_tmp;
-    }
-    auto conv3 = [&](const void* in, const std::string& wn, int act, void* out, const void* add1, const void* add2,
-                     void* out_relu) {
-      const Weight *ww = get_w(c, wn + ".w", hd), *bb = get_w(c, wn + ".b", DPT_F32);
-      if (!c.ok) return;
-      GemmOp op;
-      op.A = in; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
-      op.Wt_ptr = ww->ptr; op.N = C; op.taps = 9; op.kpad = (int)ww->shape[1] / 9;
-      op.bias = (const float*)bb->ptr; op.act = act; op.out = out; op.add1 = add1; op.add2 = add2;
-      op.out2_relu = out_relu;
-      const std::string lab = wn.substr(pre.size());
-      op.label = lab.c_str();
-      add_gemm(c, op);
-    };
-    const void* t = r;
-    const void* tr = r_relu;
-    if (lvl < 3) {
-      // conv_reassembly (ResidualConv2D) + previous fusion
-      conv3(r_relu, pre + "rcu1.c1", ACT_RELU, a_relu, nullptr, nullptr, nullptr);
-      conv3(a_relu, pre + "rcu1.c2", ACT_NONE, t_buf, r, f_prev, t_relu);
-      t = t_buf;
-      tr = t_relu;
-    }
-    // scale_proj_seq: ResidualConv2D -> (1x1 projection, x2 upsample)
-    conv3(tr, pre + "rcu2.c1", ACT_RELU, a_relu, nullptr, nullptr, nullptr);
-    conv3(a_relu, pre + "rcu2.c2", ACT_NONE, v_buf, t, nullptr, nullptr);
-    {
-      const Weight *ww = get_w(c, pre + "out.w", hd), *bb = get_w(c, pre + "out.b", DPT_F32);
-      if (!c.ok) return false;
-      GemmOp op;
-      op.A = v_buf; op.B = B; op.Ht = h; op.Wt = w; op.C = C;
-      op.Wt_ptr = ww->ptr; op.N = C; op.taps = 1; op.kpad = (int)ww->shape[1];
-      op.bias = (const float*)bb->ptr; op.out = w_buf; op.label = "out1x1";
-      add_gemm(c, op);
-    }
     void* up = lvl == 0 ? fused : f_bufs[lvl & 1];
-    add_resize(c, w_buf, up, B, h, w, 2 * h, 2 * w, C);
+    build_fusion_level(c, lvl, maps[lvl], maps_relu_in ? maps_relu_in[lvl] : nullptr, f_prev, up, B, h0 >> lvl, w0 >> lvl);
     f_prev = up;
   }
   c.ar.reset(mk);
@@ -1728,6 +1771,21 @@ int dpt_fusion(dpt_handle h, const void* const maps[4], void* fused, void* ws, s
                          const int k = map0_scale_num(c.m->cfg);
                          return build_fusion(c, maps, nullptr, fused, B, gh * k, gw * k);
                        });
+}
+int dpt_fusion_block(dpt_handle h, int level, const void* reasm_map, const void* prev_fused, void* out, void* ws,
+                     size_t ws_bytes, int B, int map_h, int map_w, void* stream) {
+  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) {
+    return build_fusion_level(c, level, reasm_map, nullptr, prev_fused, out, B, map_h, map_w);
+  });
+}
+int dpt_encoder_capture(dpt_handle h, const void* tokens, void* const taps[4], void* const* probs, void* const* block_out,
+                        int num_blocks, void* ws, size_t ws_bytes, int B, int gh, int gw, void* stream) {
+  return build_and_run(h, ws, ws_bytes, stream, [&](Ctx& c) {
+    c.cap_probs = probs;
+    c.cap_block_out = block_out;
+    c.cap_blocks = num_blocks;
+    return stage_encoder(c, tokens, taps, B, gh, gw);
+  });
 }
 int dpt_head(dpt_handle h, const void* fused, void* depth, void* ws, size_t ws_bytes, int B, int gh, int gw,
              void* stream) {

@@ -531,4 +531,51 @@ __global__ void post_u8_kernel(const T* __restrict__ depth, const float* __restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Debug / experiments: the attention probabilities softmax(scale * q k^T + bias) of one block,
+// materialised as [Bt, H, N, N] so that nn.Softmax forward hooks (demo_helpers/model_capture.py:15-61,
+// experiments/attention_visualization.py:324-332) receive what the reference's manual attention path hands them
+// (transformer_block.py:127-132). Plain CUDA-core kernel, never on the forward path: one CTA per (query row, head,
+// batch); the row's logits are recomputed in each of the three passes (max, sum, write).
+template <typename T>
+__global__ void attn_probs_kernel(const T* __restrict__ qkv, const T* __restrict__ bias, long long ldb, int wmod,
+                                  T* __restrict__ probs, int N, int H, int HD, float scale) {
+  extern __shared__ float att_q[];  // [HD]
+  __shared__ float red[32];
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int F = H * HD;
+  const T* base = qkv + (long long)b * N * 3 * F;
+  for (int d = threadIdx.x; d < HD; d += blockDim.x) att_q[d] = to_f32(base[(long long)i * 3 * F + h * HD + d]) * scale;
+  __syncthreads();
+  const T* brow = bias ? bias + (((long long)(b % wmod) * H + h) * N + i) * ldb : nullptr;
+  auto logit = [&](int j) {
+    const T* k = base + (long long)j * 3 * F + F + h * HD;
+    float acc = 0.f;
+    for (int d = 0; d < HD; ++d) acc = fmaf(att_q[d], to_f32(k[d]), acc);
+    return brow ? acc + to_f32(brow[j]) : acc;
+  };
+  auto block_reduce = [&](float v, bool is_max) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const float w = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? fmaxf(v, w) : v + w;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = is_max ? -INFINITY : 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+    __syncthreads();
+    return r;
+  };
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) m = fmaxf(m, logit(j));
+  m = block_reduce(m, true);
+  float l = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) l += __expf(logit(j) - m);
+  l = block_reduce(l, false);
+  const float inv = 1.0f / l;
+  T* out = probs + (((long long)b * H + h) * N + i) * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) out[j] = from_f32<T>(__expf(logit(j) - m) * inv);
+}
+
 }  // namespace dpt

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from .module_tree import FusionModel, ImageEncoder
 from .weights import pack_beit, pack_depthanything_v2, pack_swinv2
 
 _TORCH_TO_DPT = {torch.float16: N.DPT_F16, torch.bfloat16: N.DPT_BF16}
@@ -123,9 +124,9 @@ class DPTModel(torch.nn.Module):
         self._ws_key = None
         self._io = {}
         self.patch_embed = _PatchEmbedStage(self, self._stage_patch_embed)
-        self.imgencoder = _Stage(self, self._stage_encoder)
+        self.imgencoder = ImageEncoder(self)  # nn.Modules with hook points / per-block callables (module_tree.py)
         self.reassemble = _Stage(self, self._stage_reassemble)
-        self.fusion = _Stage(self, self._stage_fusion)
+        self.fusion = FusionModel(self)
         self.head = _Stage(self, self._stage_head)
         self.eval()
 
@@ -178,7 +179,12 @@ class DPTModel(torch.nn.Module):
 
     def _require_ready(self):
         if self._handle is None:
-            raise RuntimeError("model is not on a GPU yet: call .to('cuda') first (there is no CPU fallback)")
+            # The reference's examples use the model right after make_dpt_from_state_dict() (on the CPU, in fp32 -
+            # simple_examples/depth_prediction.py:32-33). There is no CPU path here: with a GPU present the model places
+            # itself on the current CUDA device in bf16 on first use, without one it raises.
+            if not torch.cuda.is_available():
+                raise RuntimeError("model is not on a GPU yet: call .to('cuda') first (there is no CPU fallback)")
+            self.to(device="cuda")
         return self._device, self._dtype
 
     def _materialise(self):
@@ -404,7 +410,9 @@ class DPTModel(torch.nn.Module):
         N.check(rc, self._handle, "dpt_patch_embed")
         return tokens, (gh, gw)
 
-    def _stage_encoder(self, patch_tokens: torch.Tensor, patch_grid_hw):
+    def _stage_encoder(self, patch_tokens: torch.Tensor, patch_grid_hw, capture=None):
+        """capture = (probs, block_outs): per-block output tensors or None (module_tree.ImageEncoder, debug only)"""
+        self._require_ready()
         gh, gw = int(patch_grid_hw[0]), int(patch_grid_hw[1])
         B, Np, F = patch_tokens.shape
         assert Np == gh * gw and patch_tokens.dtype == self._dtype
@@ -415,9 +423,17 @@ class DPTModel(torch.nn.Module):
             taps = [torch.empty((B, Np + 1, F), dtype=self._dtype, device=self._device) for _ in range(4)]
         ws = self._stage_ws(B, gh, gw)
         with torch.cuda.device(self._device):
-            rc = N.lib().dpt_encoder(self._handle, C.c_void_p(tok.data_ptr()), C.byref(N.ptr4(taps)),
-                                     C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
-        N.check(rc, self._handle, "dpt_encoder")
+            if capture is None:
+                rc = N.lib().dpt_encoder(self._handle, C.c_void_p(tok.data_ptr()), C.byref(N.ptr4(taps)),
+                                         C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+            else:
+                probs, outs = capture
+                n = len(probs)
+                p_arr = (C.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in probs])
+                o_arr = (C.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in outs])
+                rc = N.lib().dpt_encoder_capture(self._handle, C.c_void_p(tok.data_ptr()), C.byref(N.ptr4(taps)), p_arr, o_arr,
+                                                 n, C.c_void_p(ws.data_ptr()), ws.numel(), B, gh, gw, self._stream())
+        N.check(rc, self._handle, "dpt_encoder" if capture is None else "dpt_encoder_capture")
         return tuple(taps)
 
     def _nhwc_empty(self, B, Cc, H, W):

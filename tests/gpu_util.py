@@ -1,5 +1,7 @@
 """helpers for the -m gpu tests: call the C ABI operators on torch CUDA tensors"""
 import ctypes as C
+import json
+import os
 
 import torch
 
@@ -67,3 +69,28 @@ def resize(x, OH, OW):
 def rel_err(a, b):
     a, b = a.float(), b.float()
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item(), (a - b).abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parity gates: every tolerance of the -m gpu parity tests lives in tests/golden/parity_gates.json as
+# {name: {"measured": value on B200, "limit": <= 1.5 x measured}} (tools/make_parity_gates.py writes it from the log a
+# GPU run leaves in gpurun_out/parity_gates.jsonl). A name without an entry falls back to the loose default passed by
+# the test and is reported, so a new test can be measured once before its gate is pinned.
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_GATES_PATH = os.path.join(_ROOT, "tests", "golden", "parity_gates.json")
+_GATES = json.load(open(_GATES_PATH)) if os.path.exists(_GATES_PATH) else {}
+
+
+def gate(name: str, value: float, default_limit: float) -> float:
+    """assert value < gate(name); logs (name, value, limit) for tools/make_parity_gates.py"""
+    entry = _GATES.get(name)
+    limit = entry["limit"] if entry else default_limit
+    try:
+        os.makedirs(os.path.join(_ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(_ROOT, "gpurun_out", "parity_gates.jsonl"), "a") as f:
+            f.write(json.dumps({"name": name, "value": value, "limit": limit, "pinned": entry is not None}) + "\n")
+    except OSError:
+        pass
+    print(f"gate {name}: {value:.3e} (limit {limit:.3e}{'' if entry else ', UNPINNED default'})")
+    assert value < limit, f"{name}: {value:.3e} is not below its gate {limit:.3e}"
+    return value

@@ -11,12 +11,20 @@ import tempfile
 import pytest
 import torch
 
+from gpu_util import gate
+
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
+# loose defaults for a gate that has not been pinned yet; the real limits (<= 1.5 x the value measured on B200) live in
+# tests/golden/parity_gates.json, see gpu_util.gate
 REL_L2 = {torch.bfloat16: 1.5e-2, torch.float16: 3e-3}
 DEPTH_MAXREL = {torch.bfloat16: 3e-2, torch.float16: 5e-3}
+
+
+def _dt(dtype):
+    return "bf16" if dtype == torch.bfloat16 else "fp16"
 
 
 def _load_model(sd, dtype, name="depth_anything_v2_synth.pth"):
@@ -78,9 +86,8 @@ def test_tiny_stagewise_against_reference_golden(name, dtype):
     for k, v in report.items():
         print(f"{name} {dtype} {k}: rel_l2={v[0]:.3e} max_abs={v[1]:.3e} max_rel={v[2]:.3e}")
     for k, v in report.items():
-        tol = REL_L2[dtype] * (2.0 if k == "depth_e2e" else 1.0)
-        assert v[0] < tol, (k, v)
-    assert report["depth_e2e"][2] < DEPTH_MAXREL[dtype], report["depth_e2e"]
+        gate(f"dav2.{name}.{_dt(dtype)}.{k}.rel_l2", v[0], REL_L2[dtype] * (2.0 if k == "depth_e2e" else 1.0))
+    gate(f"dav2.{name}.{_dt(dtype)}.depth_e2e.max_rel", report["depth_e2e"][2], DEPTH_MAXREL[dtype])
 
 
 @pytest.mark.parametrize("name", ["vits_a.pt", "vits_b.pt"])
@@ -104,10 +111,10 @@ def test_vits_against_reference_golden(name):
     for i in range(4):
         ei = _err(sub(taps[i].float().cpu()), fix["taps_sub"][i])
         print(f"{name} tap{i}(sub): rel_l2={ei[0]:.3e}")
-        assert ei[0] < 3e-2, (i, ei)
-    assert et[0] < REL_L2[dtype]
-    assert e[0] < 2 * REL_L2[dtype], e
-    assert e[2] < DEPTH_MAXREL[dtype], e
+        gate(f"dav2.{name}.bf16.tap{i}_sub.rel_l2", ei[0], 3e-2)
+    gate(f"dav2.{name}.bf16.tokens_sub.rel_l2", et[0], REL_L2[dtype])
+    gate(f"dav2.{name}.bf16.depth.rel_l2", e[0], 2 * REL_L2[dtype])
+    gate(f"dav2.{name}.bf16.depth.max_rel", e[2], DEPTH_MAXREL[dtype])
 
 
 def test_vits_504_against_oracle():
@@ -124,8 +131,8 @@ def test_vits_504_against_oracle():
         e = _err(depth, ref)
         print(f"vits504 {dtype}: rel_l2={e[0]:.3e} max_abs={e[1]:.3e} max_rel={e[2]:.3e}")
         assert tuple(depth.shape) == (1, 504, 504)
-        assert e[0] < 2 * REL_L2[dtype], e
-        assert e[2] < DEPTH_MAXREL[dtype], e
+        gate(f"dav2.vits504.{_dt(dtype)}.depth.rel_l2", e[0], 2 * REL_L2[dtype])
+        gate(f"dav2.vits504.{_dt(dtype)}.depth.max_rel", e[2], DEPTH_MAXREL[dtype])
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -147,9 +154,9 @@ def test_wide_reassembly_merged_conv_transpose_against_oracle(dtype):
         assert tuple(maps[i].shape) == tuple(ref["maps"][i].shape)
         e = _err(maps[i], ref["maps"][i])
         print(f"tiny_r256 {dtype} map{i}: rel_l2={e[0]:.3e}")
-        assert e[0] < REL_L2[dtype], (i, e)
+        gate(f"dav2.tiny_r256.{_dt(dtype)}.map{i}.rel_l2", e[0], REL_L2[dtype])
     e = _err(depth, ref["depth"])
-    assert e[0] < 2 * REL_L2[dtype], e
+    gate(f"dav2.tiny_r256.{_dt(dtype)}.depth.rel_l2", e[0], 2 * REL_L2[dtype])
 
 
 def test_head_variants_fused_resize_and_generic_conv_agree_with_default():
@@ -265,8 +272,8 @@ def test_beit_tiny_stagewise_against_reference_golden(name, dtype):
     for k, v in report.items():
         print(f"{name} {dtype} {k}: rel_l2={v[0]:.3e} max_abs={v[1]:.3e} max_rel={v[2]:.3e}")
     for k, v in report.items():
-        tol = REL_L2[dtype] * (2.0 if k == "depth_e2e" else 1.0)
-        assert v[0] < tol, (k, v)
+        gate(f"beit.{name}.{_dt(dtype)}.{k}.rel_l2", v[0], REL_L2[dtype] * (2.0 if k == "depth_e2e" else 1.0))
+    gate(f"beit.{name}.{_dt(dtype)}.depth_e2e.max_rel", report["depth_e2e"][2], DEPTH_MAXREL[dtype])
 
 
 def test_beit_base_384_against_oracle():
@@ -283,7 +290,8 @@ def test_beit_base_384_against_oracle():
     e = _err(depth, ref)
     print(f"beit_base_384 bf16: rel_l2={e[0]:.3e} max_abs={e[1]:.3e} max_rel={e[2]:.3e}")
     assert tuple(depth.shape) == (2, 384, 384)
-    assert e[0] < 2 * REL_L2[torch.bfloat16], e
+    gate("beit.base384.bf16.depth.rel_l2", e[0], 2 * REL_L2[torch.bfloat16])
+    gate("beit.base384.bf16.depth.max_rel", e[2], DEPTH_MAXREL[torch.bfloat16])
 
 
 # ------------------------------------------------------------------------------------------------ MiDaS v3.1 SwinV2
@@ -329,7 +337,7 @@ def test_swinv2_micro_stagewise_against_reference_golden(name, dtype):
     e2e_tol = {torch.bfloat16: 0.08, torch.float16: 0.02}[dtype]
     for k, v in report.items():
         tol = enc_tol if k.startswith("tap") else (e2e_tol if k == "depth_e2e" else REL_L2[dtype])
-        assert v[0] < tol, (k, v)
+        gate(f"swin.{name}.{_dt(dtype)}.{k}.rel_l2", v[0], tol)
 
 
 def test_swinv2_micro_mild_logit_scale_tight_tolerance():
@@ -349,10 +357,11 @@ def test_swinv2_micro_mild_logit_scale_tight_tolerance():
         for i in range(4):
             e = _err(taps[i], st["taps"][i])
             print(f"swinv2 mild {shape} tap{i}: rel_l2={e[0]:.3e}")
-            assert e[0] < 2 * REL_L2[torch.float16], (i, e)
+            gate(f"swin.mild.{shape[1]}x{shape[2]}.fp16.tap{i}.rel_l2", e[0], 2 * REL_L2[torch.float16])
         e = _err(depth, st["depth"])
         print(f"swinv2 mild {shape} depth: rel_l2={e[0]:.3e} max_rel={e[2]:.3e}")
-        assert e[0] < 2 * REL_L2[torch.float16], e
+        gate(f"swin.mild.{shape[1]}x{shape[2]}.fp16.depth.rel_l2", e[0], 2 * REL_L2[torch.float16])
+        gate(f"swin.mild.{shape[1]}x{shape[2]}.fp16.depth.max_rel", e[2], DEPTH_MAXREL[torch.float16])
 
 
 def test_swinv2_tiny_256_against_oracle():
@@ -369,4 +378,5 @@ def test_swinv2_tiny_256_against_oracle():
     e = _err(depth, ref)
     print(f"swinv2_tiny_256 fp16: rel_l2={e[0]:.3e} max_abs={e[1]:.3e} max_rel={e[2]:.3e}")
     assert tuple(depth.shape) == (2, 256, 256)
-    assert e[0] < 0.03, e  # clamp-reaching logit scales, see the note in the micro test
+    gate("swin.tiny256.fp16.depth.rel_l2", e[0], 0.03)  # clamp-reaching logit scales, see the note in the micro test
+    gate("swin.tiny256.fp16.depth.max_rel", e[2], 0.06)

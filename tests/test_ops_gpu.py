@@ -204,6 +204,48 @@ def test_attention_head_dim_32_with_window_bias():
     assert rel < 1e-2, (rel, mx)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention_swinv2_large_window_24(dtype):
+    """config W's real attention shape: 24 x 24 windows = 576 tokens (nine 64-column kv steps), 32 features per head,
+    per-window additive tables (bias + shift mask, -100 on masked pairs, b % n_windows) - windowed_attention.py:65-123"""
+    from gpu_util import attention, gate, rel_err
+
+    nW, B, N, heads = 4, 2, 576, 6
+    Fd = heads * 32
+    g = torch.Generator(device="cpu").manual_seed(77)
+    q = torch.nn.functional.normalize(torch.randn(B * nW, N, heads, 32, generator=g), dim=-1) * 10.0  # cosine logits * scale
+    k = torch.nn.functional.normalize(torch.randn(B * nW, N, heads, 32, generator=g), dim=-1)
+    v = torch.randn(B * nW, N, heads, 32, generator=g)
+    qkv = torch.stack([q, k, v], dim=2).reshape(B * nW, N, 3 * Fd).to("cuda", dtype)
+    bias = 16 * torch.sigmoid(torch.randn(nW, heads, N, N, generator=g))
+    mask = (torch.rand(nW, 1, N, N, generator=g) < 0.3).float() * -100.0
+    mask[0] = 0  # the unshifted window has no mask
+    bias = (bias + mask).to("cuda", dtype)
+    out = attention(qkv, heads, 1.0, bias=bias, head_dim=32, bias_wmod=nW)
+    qf, kf, vf = qkv.float().reshape(B * nW, N, 3, heads, 32).permute(2, 0, 3, 1, 4).unbind(0)
+    a = qf @ kf.transpose(-2, -1) + bias.float().repeat(B, 1, 1, 1)
+    ref = (a.softmax(-1) @ vf).transpose(1, 2).reshape(B * nW, N, Fd)
+    rel, mx = rel_err(out, ref)
+    gate(f"op.attention.swin_w24.{'bf16' if dtype == torch.bfloat16 else 'fp16'}.rel_l2", rel, 1e-2 if dtype == torch.bfloat16 else 3e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention_beit_large_shape_with_bias(dtype):
+    """config E's attention shape: 577 tokens, 16 heads of 64, one additive bias table per head (image_encoder_model.py:335-354)"""
+    from gpu_util import attention, gate, rel_err
+
+    B, N, heads = 2, 577, 16
+    Fd = heads * 64
+    qkv = _mk((B, N, 3 * Fd), dtype, 53)
+    bias = _mk((heads, N, N), dtype, 54, 2.0)
+    out = attention(qkv, heads, 0.125, bias=bias)
+    q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    a = (q * 0.125) @ k.transpose(-2, -1) + bias.float()[None]
+    ref = (a.softmax(-1) @ v).transpose(1, 2).reshape(B, N, Fd)
+    rel, mx = rel_err(out, ref)
+    gate(f"op.attention.beit_577.{'bf16' if dtype == torch.bfloat16 else 'fp16'}.rel_l2", rel, 1e-2 if dtype == torch.bfloat16 else 3e-3)
+
+
 # ---- shapes large enough for the 2-CTA (cta_group::2, 256 x 256 tile) kernel: >= 74 tile pairs
 
 

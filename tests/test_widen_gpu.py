@@ -8,10 +8,16 @@ import numpy as np
 import pytest
 import torch
 
+from gpu_util import gate
+
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-REL_L2 = {torch.bfloat16: 1.5e-2, torch.float16: 3e-3}
+REL_L2 = {torch.bfloat16: 1.5e-2, torch.float16: 3e-3}  # unpinned defaults; real limits: tests/golden/parity_gates.json
+
+
+def _dt(dtype):
+    return "bf16" if dtype == torch.bfloat16 else "fp16"
 
 
 def _load(sd, dtype, name):
@@ -45,11 +51,9 @@ def test_depth_anything_v1_taps_against_reference_golden(dtype):
         depth = model(img)
     for k, (a, b) in enumerate(zip(taps, fix["taps"])):
         e = _rel_l2(a, b)
-        print(f"v1 tap{k} rel_l2 {e:.2e}")
-        assert e < REL_L2[dtype], (k, e)
+        gate(f"dav1.tiny8.{_dt(dtype)}.tap{k}.rel_l2", e, REL_L2[dtype])
     e = _rel_l2(depth, fix["depth"])
-    print(f"v1 depth rel_l2 {e:.2e}")
-    assert e < 2 * REL_L2[dtype], e
+    gate(f"dav1.tiny8.{_dt(dtype)}.depth.rel_l2", e, 2 * REL_L2[dtype])
 
 
 def test_metric_head_against_reference_golden():
@@ -62,8 +66,7 @@ def test_metric_head_against_reference_golden():
     with torch.inference_mode():
         depth = model(fix["img"].to("cuda", torch.bfloat16))
     e = _rel_l2(depth, fix["depth"])
-    print(f"metric depth rel_l2 {e:.2e}")
-    assert e < 1.5e-2, e
+    gate("dav2.metric.bf16.depth.rel_l2", e, 1.5e-2)
     assert depth.float().min() > 0 and depth.float().max() < 1
 
 
@@ -131,8 +134,6 @@ def test_vit_giant_swiglu_against_reference_golden(dtype):
         depth = model(img)
     for k, (a, b) in enumerate(zip(taps, fix["taps"])):
         e = _rel_l2(a, b)
-        print(f"giant tap{k} {dtype} rel_l2 {e:.2e}")
-        assert e < REL_L2[dtype], (k, e)
+        gate(f"dav2.giant_tiny.{_dt(dtype)}.tap{k}.rel_l2", e, REL_L2[dtype])
     e = _rel_l2(depth, fix["depth"])
-    print(f"giant depth {dtype} rel_l2 {e:.2e}")
-    assert e < 2 * REL_L2[dtype], e
+    gate(f"dav2.giant_tiny.{_dt(dtype)}.depth.rel_l2", e, 2 * REL_L2[dtype])
