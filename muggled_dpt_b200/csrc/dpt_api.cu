@@ -50,6 +50,13 @@ struct LaunchFn {
 
 struct Plan {
   std::vector<LaunchFn> launches;
+  // launches that fill per-grid constant tables (position table, BEiT / SwinV2 bias tables): they depend on the weights
+  // and the grid only - the reference memoises them the same way (relative_positional_encoder.py:351-442,
+  // windowed_attention.py:232-260) - so they run once, when the plan is first used, and are not replayed
+  std::vector<LaunchFn> init;
+  bool init_done = false;
+  cudaGraphExec_t graph_exec = nullptr;  // the replayed launches as one CUDA graph (built on the second use)
+  int uses = 0;
   // cache key
   const void* img = nullptr;
   const void* out = nullptr;
@@ -61,6 +68,7 @@ struct Plan {
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, off = 0, peak = 0;
+  size_t top = 0;  // bytes handed out from the END of the workspace: persistent per-plan tables, never reused
   bool dry = false;
   bool overflow = false;
   void* alloc(size_t n) {
@@ -68,9 +76,15 @@ struct Arena {
     void* p = dry ? nullptr : base + off;
     off += n;
     if (off > peak) peak = off;
-    if (!dry && off > cap) overflow = true;
+    if (!dry && off + top > cap) overflow = true;
     return p;
   }
+  void* alloc_persistent(size_t n) {
+    top += (n + 1023) & ~size_t(1023);
+    if (!dry && (top > cap || peak + top > cap)) overflow = true;
+    return dry ? nullptr : base + ((cap - top) & ~size_t(1023));
+  }
+  size_t need() const { return peak + top + 2048; }
   size_t mark() const { return off; }
   void reset(size_t m) { off = m; }
 };
@@ -99,6 +113,7 @@ struct Ctx {
   dpt_model_s* m;
   Arena ar;
   std::vector<LaunchFn>* launches;  // null in dry mode
+  std::vector<LaunchFn>* init = nullptr;  // per-plan table builders (run once); null: they go to `launches`
   bool dry;
   std::string err;
   bool ok = true;
@@ -123,6 +138,14 @@ struct Ctx {
     l.flops = flops;
     l.bytes = bytes;
     launches->push_back(std::move(l));
+  }
+  // a launch that fills a per-grid constant table in persistent workspace
+  void add_init(const std::string& label, double bytes, LaunchFnRaw fn) {
+    LaunchFn l;
+    l.fn = std::move(fn);
+    l.label = label;
+    l.bytes = bytes;
+    (init ? init : launches)->push_back(std::move(l));
   }
 };
 
@@ -825,7 +848,7 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
   const long long M = (long long)B * N;
   const int hd = half_dt(c);
   const size_t mk = c.ar.mark();
-  float* pos = (float*)c.ar.alloc((size_t)N * F * 4);
+  float* pos = (float*)c.ar.alloc_persistent((size_t)N * F * 4);  // per-grid position table (BEiT: unused)
   float* x = (float*)c.ar.alloc((size_t)M * F * 4);
   void* ln = c.ar.alloc((size_t)M * F * 2);  // 16-bit copy of the residual stream (A operand of qkv / fc1)
   float* stats = (float*)c.ar.alloc((size_t)M * 2 * ((F + 63) / 64) * 8);  // per-row partial (sum, sum sq)
@@ -855,7 +878,7 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       const int bh = cfg.base_grid_h, bw = cfg.base_grid_w;
       const int is_bf16 = c.is_bf16, nsm = c.num_sms;
       const float *bp = (const float*)base->ptr, *ct = (const float*)cls_tok->ptr, *ce = (const float*)cls_emb->ptr;
-      c.add("pos_table", 0.0, (double)N * F * 4.0, [=](cudaStream_t s) {
+      c.add_init("pos_table", (double)N * F * 4.0, [=](cudaStream_t s) {
         pos_table_kernel<<<N, 128, 0, s>>>(bp, ct, ce, pos, bh, bw, gh, gw, F);
         return cudaGetLastError();
       });
@@ -869,7 +892,6 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     // BEiT: cls token only, no position embedding (v31_beit/image_encoder_model.py:77-79); per-layer bias tables
     const Weight* cls = get_w(c, "beit.cls", DPT_F32);
     if (!cls) return false;
-    bias_buf = c.ar.alloc((size_t)heads * N * ldb * 2);
     if (!c.dry) {
       const int is_bf16 = c.is_bf16, nsm = c.num_sms;
       const float* cp = (const float*)cls->ptr;
@@ -917,13 +939,14 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       // relative position bias of this layer -> [H, N, ldb] (relative_positional_encoder.py:242-309)
       const Weight* tb = get_w(c, pre + "relpos.table", DPT_F32);
       if (!tb) return false;
+      bias_buf = c.ar.alloc_persistent((size_t)heads * N * ldb * 2);  // one table per layer, built once per plan
       if (!c.dry) {
         const int is_bf16 = c.is_bf16;
         const int bh = cfg.base_grid_h, bw = cfg.base_grid_w;
         const float* tp = (const float*)tb->ptr;
         void* bb = bias_buf;
         const int ldbi = (int)ldb;
-        c.add("beit_bias_table:" + pre, 0.0, (double)heads * N * ldb * 2.0, [=](cudaStream_t s) {
+        c.add_init("beit_bias_table:" + pre, (double)heads * N * ldb * 2.0, [=](cudaStream_t s) {
           DISPATCH_T(is_bf16, (beit_bias_table_kernel<T><<<dim3(N, heads), 128, 0, s>>>(tp, (T*)bb, heads, bh, bw, gh, gw, ldbi)));
           return cudaGetLastError();
         });
@@ -1090,8 +1113,6 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
     const int A = wh * ww, nW = (sgh / wh) * (sgw / ww);
     const long long ldb = (A + ATT_BN - 1) / ATT_BN * ATT_BN;
     const size_t mk_stage = c.ar.mark();
-    float* table = (float*)c.ar.alloc((size_t)(2 * wh - 1) * (2 * ww - 1) * heads * 4);
-    void* bias = c.ar.alloc((size_t)nW * heads * A * ldb * 2);
     const int pre_w = cfg.pretrained_window[st];
     const float div_h = (float)std::max((pre_w > 0 ? pre_w : wh) - 1, 1), div_w = (float)std::max((pre_w > 0 ? pre_w : ww) - 1, 1);
     for (int bi = 0; bi < cfg.layers_per_stage[st] && c.ok; ++bi) {
@@ -1107,6 +1128,10 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
       const Weight *f1w = get_w(c, pre + "fc1.w", hd), *f1b = get_w(c, pre + "fc1.b", DPT_F32);
       const Weight *f2w = get_w(c, pre + "fc2.w", hd), *f2b = get_w(c, pre + "fc2.b", DPT_F32);
       if (!c.ok) return false;
+      // continuous-position-bias table and bias (+ shift mask) tables of this block: per-grid constants, built once per plan
+      const int n_wm_alloc = shifted ? nW : 1;
+      float* table = (float*)c.ar.alloc_persistent((size_t)(2 * wh - 1) * (2 * ww - 1) * heads * 4);
+      void* bias = c.ar.alloc_persistent((size_t)n_wm_alloc * heads * A * ldb * 2);
       SwinWin w{sgh, sgw, wh, ww, shifted ? sh : 0, shifted ? sw : 0};
       SwinMaskSlices ms{};
       swin_mask_slices_axis(sgh, wh, sh, ms.h0, ms.h1);
@@ -1122,11 +1147,11 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
           DISPATCH_T(is_bf16, (swin_window_gather_kernel<T><<<grid, 256, 0, s>>>(xin, (T*)xw, w, B, F)));
           return cudaGetLastError();
         });
-        c.add("cpb_table:" + pre, 0.0, 0.0, [=](cudaStream_t s) {
+        c.add_init("cpb_table:" + pre, 0.0, [=](cudaStream_t s) {
           swin_cpb_table_kernel<<<(2 * wh - 1) * (2 * ww - 1), 256, 0, s>>>(w1p, b1p, w2p, table, wh, ww, heads, div_h, div_w);
           return cudaGetLastError();
         });
-        c.add("swin_bias:" + pre, 0.0, (double)n_wm * heads * A * ldb * 2.0, [=](cudaStream_t s) {
+        c.add_init("swin_bias:" + pre, (double)n_wm * heads * A * ldb * 2.0, [=](cudaStream_t s) {
           DISPATCH_T(is_bf16, (swin_bias_kernel<T><<<dim3(A, heads, n_wm), 128, 0, s>>>(table, (T*)bias, w, ms, heads, sh_i, ldbi)));
           return cudaGetLastError();
         });
@@ -1601,10 +1626,10 @@ int build_and_run(dpt_model_s* h, void* ws, size_t ws_bytes, void* stream, Build
     return c.err.rfind("missing weight", 0) == 0 ? DPT_ERR_MISSING : DPT_ERR_INVALID;
   }
   if (c.ar.overflow) {
-    h->err = "workspace too small: need " + std::to_string(c.ar.peak) + " bytes";
+    h->err = "workspace too small: need " + std::to_string(c.ar.need()) + " bytes";
     return DPT_ERR_WORKSPACE;
   }
-  return run_launches(h, launches, (cudaStream_t)stream, h->err);
+  return run_launches(h, launches, (cudaStream_t)stream, h->err);  // (one-off plan: table builders run in line)
 }
 
 }  // namespace
@@ -1646,6 +1671,7 @@ int dpt_create(const dpt_config* cfg, dpt_handle* out) {
 
 void dpt_destroy(dpt_handle h) {
   if (!h) return;
+  if (h->fwd_plan.graph_exec) cudaGraphExecDestroy(h->fwd_plan.graph_exec);
   for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
   delete h;
 }
@@ -1695,7 +1721,7 @@ int dpt_set_weight(dpt_handle h, const char* name, const void* dev_ptr, const in
     w.ptr = v.data();
   }
   h->weights[name] = w;
-  h->fwd_plan.valid = false;
+  h->fwd_plan.valid = false;  // (the next dpt_forward rebuilds the plan, its tables and its graph)
   return DPT_OK;
 }
 
@@ -1706,8 +1732,50 @@ int dpt_workspace_bytes(dpt_handle h, int B, int H, int W, size_t* bytes) {
     h->err = c.err;
     return c.err.rfind("missing weight", 0) == 0 ? DPT_ERR_MISSING : DPT_ERR_INVALID;
   }
-  *bytes = c.ar.peak + 1024;
+  *bytes = c.ar.need();
   return DPT_OK;
+}
+
+// DPT_GRAPH=0 replays a plan launch by launch instead of as one CUDA graph (A/B switch for tools/)
+static bool graph_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_GRAPH");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static void destroy_plan_graph(Plan& pl) {
+  if (pl.graph_exec) {
+    cudaGraphExecDestroy(pl.graph_exec);
+    pl.graph_exec = nullptr;
+  }
+}
+
+// Capture the plan's launches (programmatic-dependent-launch attributes included: they become programmatic graph
+// edges) into one executable graph. Runs on a private capture stream in thread-local mode, so nothing else the
+// process does is recorded; a failure leaves the plan on the launch-by-launch path.
+static bool capture_plan_graph(dpt_model_s* h, Plan& pl) {
+  cudaStream_t cs = nullptr;
+  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return false;
+  bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (ok) {
+    for (auto& f : pl.launches)
+      if (f(cs) != cudaSuccess) { ok = false; break; }
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cs, &g);  // must be called even after a failed launch
+    ok = ok && e == cudaSuccess && g != nullptr;
+    if (ok) ok = cudaGraphInstantiate(&pl.graph_exec, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+  }
+  cudaStreamDestroy(cs);
+  if (!ok) {
+    cudaGetLastError();  // clear the sticky-free error state of the failed capture
+    pl.graph_exec = nullptr;
+  }
+  (void)h;
+  return ok;
 }
 
 int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_bytes, int B, int H, int W,
@@ -1719,19 +1787,51 @@ int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_
   if (!(pl.valid && pl.img == img && pl.out == depth && pl.ws == ws && pl.B == B && pl.H == H && pl.W == W)) {
     pl.valid = false;
     pl.launches.clear();
+    pl.init.clear();
+    pl.init_done = false;
+    pl.uses = 0;
+    destroy_plan_graph(pl);
     Ctx c = make_ctx(h, ws, ws_bytes, &pl.launches, false);
+    c.init = &pl.init;
     if (!build_forward(c, img, depth, B, H, W)) {
       h->err = c.err;
       return c.err.rfind("missing weight", 0) == 0 ? DPT_ERR_MISSING : DPT_ERR_INVALID;
     }
     if (c.ar.overflow) {
-      h->err = "workspace too small: need " + std::to_string(c.ar.peak) + " bytes";
+      h->err = "workspace too small: need " + std::to_string(c.ar.need()) + " bytes";
       return DPT_ERR_WORKSPACE;
     }
     pl.img = img; pl.out = depth; pl.ws = ws; pl.B = B; pl.H = H; pl.W = W;
     pl.valid = true;
   }
-  return run_launches(h, pl.launches, (cudaStream_t)stream, h->err);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!pl.init_done) {
+    // per-grid tables: once per plan, ahead of the first forward on the same stream
+    for (auto& f : pl.init) {
+      const cudaError_t e = f(s);
+      if (e != cudaSuccess) {
+        h->err = std::string("kernel launch failed (") + f.label + "): " + cudaGetErrorString(e);
+        return DPT_ERR_CUDA;
+      }
+    }
+    pl.init_done = true;
+  }
+  ++pl.uses;
+  // first use: launch by launch (this also opts every kernel into its shared-memory size on this device); second use:
+  // capture; afterwards: one cudaGraphLaunch per forward. Per-launch profiling needs the launch-by-launch path.
+  if (graph_enabled() && !h->profiling && pl.uses >= 2) {
+    if (!pl.graph_exec && pl.uses == 2) capture_plan_graph(h, pl);
+    if (pl.graph_exec) {
+      const cudaError_t e = cudaGraphLaunch(pl.graph_exec, s);
+      if (e != cudaSuccess) {
+        h->err = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e);
+        return DPT_ERR_CUDA;
+      }
+      h->last_launches = (int)pl.launches.size();
+      return DPT_OK;
+    }
+  }
+  return run_launches(h, pl.launches, s, h->err);
 }
 
 int dpt_forward_host(dpt_handle h, const void* host_img, void* host_depth, void* dev_img, void* dev_depth, void* ws,
