@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--size", type=int, default=504)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--collective", default="c-abi", choices=["c-abi", "torch"],
+                    help="N > 1: the depth all-gather through dpt_allgather_depth (own ncclComm_t) or torch.distributed")
     ap.add_argument("--cpu-baseline-frames", type=int, default=16, help="bounded CPU sample: frames of B=1 (about 10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -359,11 +361,38 @@ def main():
     gathered = torch.empty(b_global, S, S, dtype=dtype, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # the path's one collective: through the library's own C entry point (a communicator created on the NCCL this
+    # process carries), torch.distributed as the fallback
+    native_gather, collective = None, "none"
+    if world > 1:
+        collective = "torch.distributed all_gather_into_tensor"
+        if args.collective == "c-abi" and args.scaling == "strong":
+            try:
+                from muggled_dpt_b200.distributed import NativeDepthAllGather
+
+                native_gather = NativeDepthAllGather()
+                collective = "dpt_allgather_depth (C ABI, own ncclComm_t)"
+            except Exception as e:  # noqa: BLE001 - any failure here must not cost the run
+                native_gather = None
+                collective += f" (dpt_allgather_depth unavailable: {type(e).__name__}: {e})"
+        ok = torch.tensor([1 if native_gather is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and native_gather is not None:  # all ranks or none
+            native_gather.close()
+            native_gather = None
+            collective = "torch.distributed all_gather_into_tensor"
+
+    def gather(local):
+        if native_gather is not None:
+            native_gather(local, gathered)
+        else:
+            all_gather_depth(local, b_global, out=gathered)
+
     def step():
         flush.zero_()  # L2 flush between iterations (B200_PROFILING.md timing hygiene)
         model.forward_into(img, out)
         if world > 1:
-            all_gather_depth(out, b_global, out=gathered)
+            gather(out)
 
     def barrier():
         if world > 1:
@@ -404,7 +433,7 @@ def main():
             def step_host():
                 model.forward_host(host_img, host_out)
                 if world > 1:
-                    all_gather_depth(model._io[(b_local, S, S)][1], b_global, out=gathered)
+                    gather(model._io[(b_local, S, S)][1])
             for _ in range(2):
                 step_host()
             ms_e2e = timed(step_host, args.steps)
@@ -479,6 +508,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args.model, b_global, b_local, world, S, args.dtype),
+            "collective": collective,
             "value_path": "DPTModel.forward_into on caller-owned device buffers (model(x) adds one input copy_ and one "
                           "output clone, ~65 MB of device copies at B=32)",
             "clocks": clocks,
@@ -496,6 +526,8 @@ def main():
         print(json.dumps(line), flush=True)
 
     if world > 1:
+        if native_gather is not None:
+            native_gather.close()
         dist.destroy_process_group()
 
 

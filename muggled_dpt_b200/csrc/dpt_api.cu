@@ -399,6 +399,8 @@ struct GemmOp {
   float* stats_out = nullptr;         // [rows, *stats_parts, 2]; room for 2 * ceil(N / 64) parts per row
   int* stats_parts = nullptr;         // receives the number of parts this GEMM writes per row
   void* out16 = nullptr;              // 16-bit copy of the fp32 output
+  const float* qk_logit = nullptr;    // SwinV2: cosine-normalise q / k heads (32 columns each) in the epilogue, q *= logit[h]
+  int qk_features = 0;
   const float* head_w = nullptr;      // host pointer to 32 floats (OUT_HEAD)
   float head_b = 0.f;
   int head_act = ACT_RELU;
@@ -494,6 +496,12 @@ bool add_gemm(Ctx& c, GemmOp op) {
     p.stats_out = op.stats_out; p.stats_parts = 2 * p.n_tiles; *op.stats_parts = p.stats_parts;
     p.out16 = op.out16; p.ld_out16 = op.ldo;
   }
+  if (op.qk_logit != nullptr) {
+    if (op.out_kind != OUT_HALF || op.act != ACT_NONE || op.qk_features % 32 != 0 || op.N != 3 * op.qk_features)
+      return c.fail("gemm: q/k normalisation needs a 16-bit [q|k|v] output with 32 features per head");
+    p.qk_logit = op.qk_logit;
+    p.qk_features = op.qk_features;
+  }
   if (op.head_w) memcpy(p.head_w, op.head_w, 32 * sizeof(float));
   p.head_b = op.head_b;
   p.head_act = op.head_act;
@@ -501,6 +509,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
   const long long total = (long long)p.B * p.tiles_y * p.tiles_x * p.n_tiles;
   int grid = (int)std::min<long long>(total, c.num_sms);
   if (two_cta) grid = (int)std::min<long long>(2 * ((m_tiles_all + 1) / 2) * n_tiles_all, c.num_sms & ~1);
+
   {
     const double pix = (double)op.B * op.H * op.W;
     const double flops = 2.0 * pix * op.N * op.C * op.taps;
@@ -1098,10 +1107,10 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
         const void* yin = y;
         const float eps = cfg.ln_eps;
         c.add("ln_merge:" + mp, 0.0, (double)Mn * F * 6.0, [=](cudaStream_t s) {
-          const unsigned grid = (unsigned)((Mn + 7) / 8);
           SwinWin w0{};
-          DISPATCH_T(is_bf16, (swin_ln_residual_kernel<T, 0, false><<<grid, 256, 0, s>>>((const T*)yin, lwp, lbp, xo, Mn, F, eps, w0)));
-          return cudaGetLastError();
+          cudaError_t e;
+          DISPATCH_T(is_bf16, (e = launch_swin_ln_residual<T, 0, false, 0>((const T*)yin, lwp, lbp, xo, (T*)nullptr, Mn, F, eps, w0, w0, s)));
+          return e;
         });
       }
       std::swap(x, x_next);
@@ -1133,6 +1142,10 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
       float* table = (float*)c.ar.alloc_persistent((size_t)(2 * wh - 1) * (2 * ww - 1) * heads * 4);
       void* bias = c.ar.alloc_persistent((size_t)n_wm_alloc * heads * A * ldb * 2);
       SwinWin w{sgh, sgw, wh, ww, shifted ? sh : 0, shifted ? sw : 0};
+      // the NEXT block of this stage (its window partition / shift is applied by this block's last kernel)
+      const bool has_next = bi + 1 < cfg.layers_per_stage[st];
+      const bool next_shifted = ((bi + 1) % 2 == 1) && (sh > 0 || sw > 0);
+      SwinWin wn{sgh, sgw, wh, ww, next_shifted ? sh : 0, next_shifted ? sw : 0};
       SwinMaskSlices ms{};
       swin_mask_slices_axis(sgh, wh, sh, ms.h0, ms.h1);
       swin_mask_slices_axis(sgw, ww, sw, ms.w0, ms.w1);
@@ -1142,11 +1155,15 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
         const float* xin = x;
         const float *w1p = (const float*)c1->ptr, *b1p = (const float*)cb->ptr, *w2p = (const float*)c2->ptr;
         const int ldbi = (int)ldb, sh_i = shifted ? 1 : 0;
-        c.add("window_gather:" + pre, 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
-          const int grid = ew_grid(M * (F / 4), 256, nsm);
-          DISPATCH_T(is_bf16, (swin_window_gather_kernel<T><<<grid, 256, 0, s>>>(xin, (T*)xw, w, B, F)));
-          return cudaGetLastError();
-        });
+        if (bi == 0) {
+          // first block of a stage: window partition of the fp32 stream (later blocks receive their windowed 16-bit
+          // input from the previous block's post-norm kernel)
+          c.add("window_gather:" + pre, 0.0, (double)M * F * 6.0, [=](cudaStream_t s) {
+            const int grid = ew_grid(M * (F / 4), 256, nsm);
+            DISPATCH_T(is_bf16, (swin_window_gather_kernel<T><<<grid, 256, 0, s>>>(xin, (T*)xw, w, B, F)));
+            return cudaGetLastError();
+          });
+        }
         c.add_init("cpb_table:" + pre, 0.0, [=](cudaStream_t s) {
           swin_cpb_table_kernel<<<(2 * wh - 1) * (2 * ww - 1), 256, 0, s>>>(w1p, b1p, w2p, table, wh, ww, heads, div_h, div_w);
           return cudaGetLastError();
@@ -1157,20 +1174,11 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
         });
       }
       {
-        GemmOp op;
+        GemmOp op;  // qkv = xw Wqkv^T + [q_bias, 0, v_bias]; q, k heads cosine-normalised (q * logit scale) in the epilogue
         op.A = xw; op.Wt = (int)M; op.C = F; op.Wt_ptr = qw->ptr; op.N = 3 * F; op.kpad = (int)qw->shape[1];
         op.bias = (const float*)qb->ptr; op.out = qkv; op.label = "qkv";
+        op.qk_logit = (const float*)ls->ptr; op.qk_features = F;
         add_gemm(c, op);
-      }
-      if (!c.dry) {
-        const int is_bf16 = c.is_bf16;
-        const float* lsp = (const float*)ls->ptr;
-        c.add("qk_normalize:" + pre, 0.0, (double)M * F * 2.0 * 4.0, [=](cudaStream_t s) {
-          const long long warps = M * heads * 2;
-          const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
-          DISPATCH_T(is_bf16, (swin_qk_normalize_kernel<T><<<grid, 256, 0, s>>>((T*)qkv, lsp, M, F, heads)));
-          return cudaGetLastError();
-        });
       }
       if (c.cap_probs_at(blk_index)) add_attn_probs(c, qkv, bias, ldb, n_wm, c.cap_probs_at(blk_index), B * nW, A, heads, 32, 1.0f);
       add_attention(c, qkv, bias, ldb, n_wm, att, B * nW, A, heads, 32, 1.0f);
@@ -1181,18 +1189,19 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
         add_gemm(c, op);
       }
       if (!c.dry) {
+        // x[pixel(i)] += LN1(y[i]) (window-major -> image scatter) and the 16-bit copy of the new rows = fc1's input
         const int is_bf16 = c.is_bf16;
         const float *gp = (const float*)n1w->ptr, *bp = (const float*)n1b->ptr;
         float* xo = x;
         const void* yin = y;
+        void* x16 = xw;
         const float eps = cfg.ln_eps;
-        c.add("ln_residual:" + pre + "attn", 0.0, (double)M * F * 10.0, [=](cudaStream_t s) {
-          const unsigned grid = (unsigned)((M + 7) / 8);
-          DISPATCH_T(is_bf16, (swin_ln_residual_kernel<T, 1, true><<<grid, 256, 0, s>>>((const T*)yin, gp, bp, xo, M, F, eps, w)));
-          return cudaGetLastError();
+        c.add("ln_residual:" + pre + "attn", 0.0, (double)M * F * 12.0, [=](cudaStream_t s) {
+          cudaError_t e;
+          DISPATCH_T(is_bf16, (e = launch_swin_ln_residual<T, 1, true, 1>((const T*)yin, gp, bp, xo, (T*)x16, M, F, eps, w, w, s)));
+          return e;
         });
       }
-      add_cast_to_half(c, x, xw, M * F, "cast_mlp_in");
       {
         GemmOp op;
         op.A = xw; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = (int)f1w->shape[0]; op.kpad = (int)f1w->shape[1];
@@ -1206,16 +1215,22 @@ bool build_encoder_swin(Ctx& c, const void* tokens, void* const taps[4], int B, 
         add_gemm(c, op);
       }
       if (!c.dry) {
+        // x += LN2(y); the new rows also go, as 16 bits, to their window-major position for the next block's QKV GEMM
         const int is_bf16 = c.is_bf16;
         const float *gp = (const float*)n2w->ptr, *bp = (const float*)n2b->ptr;
         float* xo = x;
         const void* yin = y;
+        void* x16 = xw;
         const float eps = cfg.ln_eps;
-        c.add("ln_residual:" + pre + "mlp", 0.0, (double)M * F * 10.0, [=](cudaStream_t s) {
-          const unsigned grid = (unsigned)((M + 7) / 8);
+        c.add("ln_residual:" + pre + "mlp", 0.0, (double)M * F * (has_next ? 12.0 : 10.0), [=](cudaStream_t s) {
           SwinWin w0{};
-          DISPATCH_T(is_bf16, (swin_ln_residual_kernel<T, 0, true><<<grid, 256, 0, s>>>((const T*)yin, gp, bp, xo, M, F, eps, w0)));
-          return cudaGetLastError();
+          cudaError_t e;
+          if (has_next) {
+            DISPATCH_T(is_bf16, (e = launch_swin_ln_residual<T, 0, true, 2>((const T*)yin, gp, bp, xo, (T*)x16, M, F, eps, w0, wn, s)));
+          } else {
+            DISPATCH_T(is_bf16, (e = launch_swin_ln_residual<T, 0, true, 0>((const T*)yin, gp, bp, xo, (T*)nullptr, M, F, eps, w0, w0, s)));
+          }
+          return e;
         });
       }
       if (c.cap_block_out_at(blk_index)) add_cast_to_half(c, x, c.cap_block_out_at(blk_index), M * F, "block_out(debug)");
@@ -1619,6 +1634,9 @@ int build_and_run(dpt_model_s* h, void* ws, size_t ws_bytes, void* stream, Build
   if (!h) return DPT_ERR_INVALID;
   DeviceGuard guard(h->device);
   if (guard.err != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err); return DPT_ERR_CUDA; }
+  // a stage call lays its own tables / scratch out in the persistent end of the workspace: if the forward plan lives in
+  // the same workspace its per-grid tables have to be rebuilt before its next use
+  h->fwd_plan.init_done = false;
   std::vector<LaunchFn> launches;
   Ctx c = make_ctx(h, ws, ws_bytes, &launches, false);
   if (!fn(c)) {

@@ -76,6 +76,11 @@ struct __align__(64) GemmParams {
   int stats_parts;
   void* out16;             // 16-bit copy of the fp32 output (same pixel indexing), or null
   long long ld_out16;
+  // SwinV2 cosine attention folded into the QKV GEMM (windowed_attention.py:99-111): with 32 features per head a
+  // thread's 32-column epilogue unit is exactly one head of one token, so q <- normalize(q) * logit_scale[h] and
+  // k <- normalize(k) (F.normalize, eps 1e-12) are applied to the fp32 accumulator before its single 16-bit rounding.
+  const float* qk_logit;   // [heads] (already exp'd and clamped), or null
+  int qk_features;         // F: columns [0, F) are q, [F, 2F) k, [2F, 3F) v
   float head_w[32];   // OUT_HEAD: depth = act2(relu(acc + bias) . head_w + head_b)
   float head_b;
   int head_act;       // ACT_RELU or ACT_SIGMOID
@@ -475,6 +480,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
                 f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
               }
+              }
+              if constexpr (ACT == ACT_NONE && !F32OUT) {
+                if (p.qk_logit != nullptr) {
+                  const int gcol = n_blk * BLOCK_N + col_base + c0 + cc;  // a multiple of 32 = one head
+                  if (gcol < 2 * p.qk_features) {
+                    float ss = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) ss = fmaf(f[j], f[j], ss);
+                    float sc = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                    if (gcol < p.qk_features) sc *= __ldg(p.qk_logit + (gcol >> 5));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] *= sc;
+                  }
+                }
               }
               if constexpr (ACT == ACT_GELU) {
 #pragma unroll

@@ -1,6 +1,6 @@
-// SwinV2-specific helper kernels (v31_swinv2/*): window partition with cyclic shift, cosine-attention q/k
-// normalisation, continuous-position-bias tables (+ shift mask), post-norm LayerNorm with residual scatter,
-// patch merging gather.
+// SwinV2-specific helper kernels (v31_swinv2/*): window partition with cyclic shift, continuous-position-bias tables
+// (+ shift mask), post-norm LayerNorm with residual scatter (+ the next GEMM's 16-bit operand), patch merging gather.
+// (The cosine-attention q/k normalisation lives in the QKV GEMM's epilogue, gemm_tc.cuh qk_logit.)
 #pragma once
 #include "kernels_misc.cuh"
 
@@ -43,27 +43,6 @@ __global__ void swin_window_gather_kernel(const float* __restrict__ x, T* __rest
     T o[4] = {from_f32<T>(v.x), from_f32<T>(v.y), from_f32<T>(v.z), from_f32<T>(v.w)};
     *reinterpret_cast<uint2*>(xw + tok * C + c4 * 4) = *reinterpret_cast<uint2*>(o);
   }
-}
-
-// Cosine attention (windowed_attention.py:110-111): q <- normalize(q) * logit_scale[h], k <- normalize(k), in place
-// in the fused qkv buffer [M, 3C] (head h = columns h*32 .. +31). One warp per (token, head, q|k), one lane per dim.
-template <typename T>
-__global__ void swin_qk_normalize_kernel(T* __restrict__ qkv, const float* __restrict__ logit_scale, long long M, int C,
-                                         int heads) {
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= M * heads * 2) return;
-  const int which = (int)(warp % 2);
-  const int h = (int)((warp / 2) % heads);
-  const long long m = warp / (2 * heads);
-  T* p = qkv + m * 3 * C + which * C + h * 32 + lane;
-  const float v = to_f32(*p);
-  float ss = v * v;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
-  const float s = which == 0 ? logit_scale[h] : 1.0f;
-  *p = from_f32<T>(v * inv * s);
 }
 
 // Continuous position bias table (relative_positional_encoder.py:60-93,121-283):
@@ -131,65 +110,117 @@ __global__ void swin_bias_kernel(const float* __restrict__ table, T* __restrict_
   }
 }
 
+// image pixel row (b, y, x) -> window-major token index under window config w (inverse of swin_src_pixel)
+__device__ __forceinline__ long long swin_dst_token(const SwinWin& w, long long pix) {
+  const int x0 = (int)(pix % w.gw);
+  long long t = pix / w.gw;
+  const int y0 = (int)(t % w.gh);
+  const int b = (int)(t / w.gh);
+  const int y = (y0 - w.sh + w.gh) % w.gh, x = (x0 - w.sw + w.gw) % w.gw;  // position after roll(-shift)
+  const int nwx = w.gw / w.ww, nwy = w.gh / w.wh;
+  const int wy = y / w.wh, ty = y % w.wh, wx = x / w.ww, tx = x % w.ww;
+  return (((long long)b * nwy + wy) * nwx + wx) * (w.wh * w.ww) + ty * w.ww + tx;
+}
+
 // Post-norm residual (image_encoder_model.py:213-225): x32[dst(i), :] (+)= LayerNorm(y[i, :]) * g + b, eps 1e-5.
-// MAP: 0 identity, 1 window-major -> image (reverse partition + roll back). One warp per row.
-template <typename T, int MAP, bool ADD>
-__global__ void swin_ln_residual_kernel(const T* __restrict__ y, const float* __restrict__ g, const float* __restrict__ bia,
-                                        float* __restrict__ x, long long M, int F, float eps, SwinWin w) {
-  constexpr int MAXV = 12;  // F <= 1536
+// MAP: 0 identity, 1 window-major -> image (reverse partition + roll back). One warp per row; the residual row and the
+// LayerNorm parameters are fetched before the two reductions so that all of a row's memory traffic is in flight at once.
+// OUT16: 0 none; 1 = also write the new residual row as 16 bits at the same (image-order) row: the A operand of fc1;
+//        2 = also write it as 16 bits at its window-major position under `wn`: the A operand of the NEXT block's QKV
+//            GEMM (window partition + cyclic shift as pure addressing, windowed_attention.py:182-228,269-339).
+// LPR lanes share one row (8 / 16 / 32: narrow stages put 4 / 2 rows in a warp so the per-row index arithmetic and the
+// reductions are amortised), each lane owns up to MAXV float4 of it; a block of 256 threads handles 8 * 32 / LPR rows.
+template <typename T, int MAP, bool ADD, int OUT16, int LPR, int MAXV>
+__global__ void __launch_bounds__(256) swin_ln_residual_kernel(const T* __restrict__ y, const float* __restrict__ g,
+                                                               const float* __restrict__ bia, float* __restrict__ x,
+                                                               T* __restrict__ x16, long long M, int F, float eps,
+                                                               SwinWin w, SwinWin wn) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
-  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const T* yr = y + row * F;
-  float4 v[MAXV];
+  const int sub = lane % LPR;
+  const long long row = (blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool live = row < M;  // (dead lanes still take part in the shuffles)
+  const long long rowc = live ? row : M - 1;
+  const T* yr = y + rowc * F;
+  long long dst = rowc;
+  if (MAP == 1) {
+    int b;
+    dst = swin_src_pixel(w, rowc, b);
+  }
+  float* xr = x + dst * F;
+  float4 v[MAXV], r[MAXV];
+  uint2 raw[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int f = (i * LPR + sub) * 4;
+    if (f < F) {
+      raw[i] = *reinterpret_cast<const uint2*>(yr + f);
+      if (ADD) r[i] = *reinterpret_cast<const float4*>(xr + f);
+    }
+  }
   float sum = 0.0f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int f = i * 128 + lane * 4;
+    const int f = (i * LPR + sub) * 4;
     if (f < F) {
-      v[i] = make_float4(to_f32(yr[f]), to_f32(yr[f + 1]), to_f32(yr[f + 2]), to_f32(yr[f + 3]));
+      const T* e = reinterpret_cast<const T*>(&raw[i]);
+      v[i] = make_float4(to_f32(e[0]), to_f32(e[1]), to_f32(e[2]), to_f32(e[3]));
       sum += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / (float)F;
   float var = 0.0f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int f = i * 128 + lane * 4;
+    const int f = (i * LPR + sub) * 4;
     if (f < F) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       var += a * a + b * b + c * c + d * d;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  if (!live) return;
   const float rstd = rsqrtf(var / (float)F + eps);
-  long long dst = row;
-  if (MAP == 1) {
-    int b;
-    dst = swin_src_pixel(w, row, b);
-  }
-  float* xr = x + dst * F;
+  T* x16r = nullptr;
+  if (OUT16 == 1) x16r = x16 + dst * F;
+  if (OUT16 == 2) x16r = x16 + swin_dst_token(wn, dst) * F;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int f = i * 128 + lane * 4;
+    const int f = (i * LPR + sub) * 4;
     if (f < F) {
-      const float4 ww4 = *reinterpret_cast<const float4*>(g + f);
-      const float4 bb = *reinterpret_cast<const float4*>(bia + f);
+      const float4 ww4 = __ldg(reinterpret_cast<const float4*>(g + f));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bia + f));
       float4 o;
       o.x = (v[i].x - mean) * rstd * ww4.x + bb.x;
       o.y = (v[i].y - mean) * rstd * ww4.y + bb.y;
       o.z = (v[i].z - mean) * rstd * ww4.z + bb.z;
       o.w = (v[i].w - mean) * rstd * ww4.w + bb.w;
       if (ADD) {
-        const float4 r = *reinterpret_cast<const float4*>(xr + f);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        o.x += r[i].x; o.y += r[i].y; o.z += r[i].z; o.w += r[i].w;
       }
       *reinterpret_cast<float4*>(xr + f) = o;
+      if (OUT16 != 0) {
+        T h4[4] = {from_f32<T>(o.x), from_f32<T>(o.y), from_f32<T>(o.z), from_f32<T>(o.w)};
+        *reinterpret_cast<uint2*>(x16r + f) = *reinterpret_cast<uint2*>(h4);
+      }
     }
   }
+}
+
+// host launcher: picks the lanes-per-row split from the row length (F <= 1536, a multiple of 32)
+template <typename T, int MAP, bool ADD, int OUT16>
+cudaError_t launch_swin_ln_residual(const T* y, const float* g, const float* bia, float* x, T* x16, long long M, int F,
+                                    float eps, SwinWin w, SwinWin wn, cudaStream_t s) {
+  const int f4 = F / 4;
+  auto blocks = [&](int rows_per_block) { return (unsigned)((M + rows_per_block - 1) / rows_per_block); };
+  if (f4 <= 8 * 6) swin_ln_residual_kernel<T, MAP, ADD, OUT16, 8, 6><<<blocks(32), 256, 0, s>>>(y, g, bia, x, x16, M, F, eps, w, wn);
+  else if (f4 <= 16 * 6) swin_ln_residual_kernel<T, MAP, ADD, OUT16, 16, 6><<<blocks(16), 256, 0, s>>>(y, g, bia, x, x16, M, F, eps, w, wn);
+  else if (f4 <= 32 * 6) swin_ln_residual_kernel<T, MAP, ADD, OUT16, 32, 6><<<blocks(8), 256, 0, s>>>(y, g, bia, x, x16, M, F, eps, w, wn);
+  else swin_ln_residual_kernel<T, MAP, ADD, OUT16, 32, 12><<<blocks(8), 256, 0, s>>>(y, g, bia, x, x16, M, F, eps, w, wn);
+  return cudaGetLastError();
 }
 
 // PatchMerge gather (patch_merge.py:81-101): x32 [B, gh, gw, C] -> [B, gh/2 * gw/2, 4C] 16-bit, channel blocks in

@@ -7,8 +7,12 @@ torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests) is pl
 
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
+
+from . import _native as N
 
 
 def shard_range(global_batch: int, rank: int, world: int) -> tuple[int, int]:
@@ -56,3 +60,49 @@ def sharded_forward(model, images_global: torch.Tensor, group=None) -> torch.Ten
     lo, hi = shard_range(B, rank, world)
     local = model(images_global[lo:hi].contiguous())
     return all_gather_depth(local, B, group=group)
+
+
+class _NcclUniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+class NativeDepthAllGather:
+    """The path's one collective through the C ABI: `dpt_allgather_depth` (include/dpt_b200.h) on a communicator this
+    object owns - created with ncclCommInitRank on the NCCL library the process already carries (PyTorch's), the unique
+    id exchanged once over the existing torch.distributed group. One process per GPU; every rank must construct it."""
+
+    def __init__(self, group=None):
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._nccl = C.CDLL("libnccl.so.2", mode=C.RTLD_GLOBAL)  # resolves to the copy torch has loaded
+        self._nccl.ncclGetUniqueId.argtypes = [C.POINTER(_NcclUniqueId)]
+        self._nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _NcclUniqueId, C.c_int]
+        self._nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+        uid = _NcclUniqueId()
+        payload = [None]
+        if self.rank == 0:
+            if self._nccl.ncclGetUniqueId(C.byref(uid)) != 0:
+                raise RuntimeError("ncclGetUniqueId failed")
+            payload[0] = C.string_at(C.byref(uid), 128)
+        dist.broadcast_object_list(payload, src=0, group=group)
+        C.memmove(C.byref(uid), payload[0], 128)
+        self._comm = C.c_void_p()
+        rc = self._nccl.ncclCommInitRank(C.byref(self._comm), self.world, uid, self.rank)
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank failed with ncclResult_t {rc}")
+
+    def __call__(self, local_depth: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """local_depth [b, H, W] (same b on every rank) -> out [world * b, H, W], enqueued on the current stream"""
+        if not (local_depth.is_contiguous() and out.is_contiguous()) or out.numel() != self.world * local_depth.numel():
+            raise ValueError("all-gather buffers must be contiguous with out = world x local elements")
+        code = {torch.bfloat16: N.DPT_BF16, torch.float16: N.DPT_F16}[local_depth.dtype]
+        stream = C.c_void_p(torch.cuda.current_stream(local_depth.device).cuda_stream)
+        rc = N.lib().dpt_allgather_depth(self._comm, C.c_void_p(local_depth.data_ptr()), C.c_void_p(out.data_ptr()),
+                                         local_depth.numel(), code, stream)
+        N.check(rc, None, "dpt_allgather_depth")
+        return out
+
+    def close(self):
+        if self._comm:
+            self._nccl.ncclCommDestroy(self._comm)
+            self._comm = C.c_void_p()

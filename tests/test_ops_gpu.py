@@ -315,3 +315,4 @@ def test_conv3x3_two_cta_pairs():
     rel, mx = rel_err(out, ref)
     assert rel < 8e-3, (rel, mx)
     assert torch.equal(out_relu, torch.relu(out))
+
