@@ -44,7 +44,8 @@ namespace dpt {
 constexpr int A2_THREADS = 256;  // warpgroup 0 = softmax (4 warps), warpgroup 1 = TMA producer, MMA issuer, 2 idle
 constexpr int A2_BM = 128;       // query rows per CTA
 constexpr int A2_BN = 64;        // kv rows per step
-constexpr int A2_STAGES = 3;
+constexpr int A2_STAGES = 3;       // K/V stages without bias; with bias one of them becomes the bias tile (same 64 KB)
+constexpr int A2_BIAS_BYTES = A2_BM * A2_BN * 2;  // 16 KB: bias[q0 .. q0+127][kv0 .. kv0+63], rows of 128 B, 128B swizzle
 constexpr int A2_Q_BYTES = A2_BM * 64 * 2;   // 16 KB
 constexpr int A2_KV_BYTES = A2_BN * 64 * 2;  // 8 KB
 constexpr int A2_SMEM_BYTES = A2_Q_BYTES + 2 * A2_STAGES * A2_KV_BYTES + 256;  // 64.25 KB -> 3 CTAs per SM
@@ -118,11 +119,12 @@ DPT_DEVICE void a2_tile_of_cta(const AttnParams& p, int id, int& qt, int& h, int
 template <bool HAS_BIAS, bool BF16, int HD>
 __global__ void __launch_bounds__(A2_THREADS, 3) attn64_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int ST = A2_STAGES;
+  constexpr int ST = HAS_BIAS ? A2_STAGES - 1 : A2_STAGES;
   uint8_t* sQ = smem;
   uint8_t* sK = smem + A2_Q_BYTES;
   uint8_t* sV = sK + ST * A2_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * A2_KV_BYTES);
+  uint8_t* sBias = sV + ST * A2_KV_BYTES;  // HAS_BIAS only (the space of the third K/V stage)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_Q_BYTES + 2 * A2_STAGES * A2_KV_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;       // [ST]
   uint64_t* k_empty = k_full + ST;   // [ST]
@@ -132,7 +134,9 @@ __global__ void __launch_bounds__(A2_THREADS, 3) attn64_tc_kernel(const __grid_c
   uint64_t* s_free = s_full + 1;     // all 128 softmax threads hold their S_j row in registers
   uint64_t* p_ready = s_full + 2;    // all 128 softmax threads wrote their P_j row
   uint64_t* pv_done = s_full + 3;    // P_j V_j complete (P may be overwritten, O may be read)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 4);  // [2]
+  uint64_t* bias_full = s_full + 4;  // the bias tile of step j has landed (TMA)
+  uint64_t* bias_empty = s_full + 5; // all 128 softmax threads have read it
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 6);  // [2]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,6 +164,9 @@ __global__ void __launch_bounds__(A2_THREADS, 3) attn64_tc_kernel(const __grid_c
     mbar_init(s_free, 128);
     mbar_init(p_ready, 128);
     mbar_init(pv_done, 1);
+    mbar_init(bias_full, 1);
+    mbar_init(bias_empty, 128);
+    if constexpr (HAS_BIAS) prefetch_tmap(&p.tmBias);
     fence_barrier_init();
   }
   if (warp_idx == 5) {
@@ -194,6 +201,13 @@ __global__ void __launch_bounds__(A2_THREADS, 3) attn64_tc_kernel(const __grid_c
           mbar_wait(&v_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[s], A2_KV_BYTES);
           tma_load_3d(sV + s * A2_KV_BYTES, &p.tmQKV, &v_full[s], 2 * p.F + h * HD, j * A2_BN, b);
+          if constexpr (HAS_BIAS) {
+            // bias tile of step j (single buffer: it is consumed at the very start of the step's softmax, so the next
+            // load has almost a whole step to land). Rows / columns past N are zero-filled by TMA and masked later.
+            mbar_wait(bias_empty, (j & 1) ^ 1);
+            mbar_arrive_expect_tx(bias_full, A2_BIAS_BYTES);
+            tma_load_3d(sBias, &p.tmBias, bias_full, j * A2_BN, q0, (b % p.bias_wmod) * p.H + h);
+          }
         }
       }
       __syncwarp();
@@ -260,12 +274,9 @@ __global__ void __launch_bounds__(A2_THREADS, 3) attn64_tc_kernel(const __grid_c
     float mu = 0.0f;  // stabiliser in exp2 units (score * scale * log2e [+ bias * log2e]); >= row max - 8
     float2 l2[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};  // row sum of P, two packed accumulators
     const int qrow = q0 + r;
-    const uint16_t* bias_row = nullptr;
-    if constexpr (HAS_BIAS) {
-      // rows past N read row N-1 (never stored); ldb is a multiple of 128 so whole kv steps are in bounds
-      bias_row = reinterpret_cast<const uint16_t*>(p.bias) +
-                 (((long long)(b % p.bias_wmod) * p.H + h) * p.N + min(qrow, p.N - 1)) * p.ldb;
-    }
+    // my row of the bias tile: 128 B, its eight 16-byte chunks XOR-swizzled by (row & 7) (TMA SWIZZLE_128B), which
+    // also makes the 32 lanes' 16-byte reads conflict-free
+    const uint32_t bias_row_smem = smem_u32(sBias) + r * 128;
     const uint32_t s_addr = tmem_S + lane_addr;
     const uint32_t p_addr = tmem_P + lane_addr;
     const uint32_t o_addr = tmem_O + lane_addr;
@@ -286,13 +297,24 @@ __global__ void __launch_bounds__(A2_THREADS, 3) attn64_tc_kernel(const __grid_c
       tc_fence_before();
       mbar_arrive(s_free);  // S_{j+1} may overwrite S now
       if constexpr (HAS_BIAS) {
+        mbar_wait(bias_full, j & 1);
 #pragma unroll
         for (int ci = 0; ci < nch; ++ci) {
-          float bf[32];
-          load_bias32(bias_row + kv0 + ci * 32, bf, is_bf16);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sv[ci][i] = __float_as_uint(fmaf(__uint_as_float(sv[ci][i]), c, bf[i]));
+          for (int k = 0; k < 4; ++k) {
+            const int chunk = ci * 4 + k;  // columns chunk*8 .. +7 of the tile
+            const float4 raw = lds_f4(bias_row_smem + (uint32_t)((chunk ^ (r & 7)) << 4));
+            const uint32_t w[4] = {__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 bf = unpack2(w[t], is_bf16);
+              const int i = k * 8 + 2 * t;
+              sv[ci][i] = __float_as_uint(fmaf(__uint_as_float(sv[ci][i]), c, bf.x * 1.4426950408889634f));
+              sv[ci][i + 1] = __float_as_uint(fmaf(__uint_as_float(sv[ci][i + 1]), c, bf.y * 1.4426950408889634f));
+            }
+          }
         }
+        mbar_arrive(bias_empty);
       }
       if constexpr (MASKED) {
 #pragma unroll
@@ -385,6 +407,10 @@ __global__ void __launch_bounds__(A2_THREADS, 3) attn64_tc_kernel(const __grid_c
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(s_full, j & 1);
         mbar_arrive(s_free);
+        if constexpr (HAS_BIAS) {
+          mbar_wait(bias_full, j & 1);
+          mbar_arrive(bias_empty);
+        }
         if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
         mbar_arrive(p_ready);
       }

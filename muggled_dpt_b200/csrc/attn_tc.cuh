@@ -66,6 +66,7 @@ struct __align__(64) AttnParams {
   const void* bias;   // optional additive bias [H, N, ldb] 16-bit (BEiT relative position bias), shared over batch
   long long ldb;      // row stride of bias in elements: a multiple of 128 (whole kv tiles stay in bounds)
   int bias_wmod;      // bias table index = (batch % bias_wmod) * H + h  (SwinV2: per-window shift masks; else 1)
+  CUtensorMap tmBias; // attn64_tc.cuh: the same bias tables as a 3-D map (ldb, N, bias_wmod * H), box (64, 128, 1), 128B swizzle
 };
 
 // 32 consecutive 16-bit bias values (64 B, 16-byte aligned) -> fp32, pre-multiplied by log2(e)

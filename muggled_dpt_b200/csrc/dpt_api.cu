@@ -661,6 +661,12 @@ bool add_attention(Ctx& c, const void* qkv, const void* bias, long long ldb, int
   p.ldb = ldb;
   p.bias_wmod = wmod > 0 ? wmod : 1;
   const bool has_bias = bias != nullptr;
+  if (has_bias && !v1) {  // the bias tables as a TMA map: tile (64 kv columns, 128 query rows) of table (b % wmod) * H + h
+    uint64_t bdims[3] = {(uint64_t)ldb, (uint64_t)N, (uint64_t)p.bias_wmod * heads};
+    uint64_t bstr[2] = {(uint64_t)ldb * 2, (uint64_t)ldb * 2 * N};
+    uint32_t bbox[3] = {64, 128, 1};
+    if (!make_tmap(&p.tmBias, bias, 3, bdims, bstr, bbox, c.is_bf16, c.err)) return c.fail(c.err);
+  }
   const double flops = 4.0 * B * heads * (double)N * N * hd, bytes = 4.0 * (double)B * N * F * 2.0;
   if (v1) {
     dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
