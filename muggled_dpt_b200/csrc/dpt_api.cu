@@ -288,7 +288,10 @@ cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
 
 template <bool BF16>
 cudaError_t launch_gemm2_dt(const GemmParams& p, int bn, int grid, cudaStream_t s) {
-  if (bn == 128) {  // (chosen only for 16-bit outputs without GELU, see add_gemm)
+  if (bn == 128) {  // 256 x 128 pair tiles: 16-bit outputs without GELU (3x3 convolutions), fp32 residual outputs (small M)
+    if (p.out_kind == OUT_F32)
+      return use_respf(p) ? launch_gemm2_inst<OUT_F32, ACT_NONE, BF16, true, 128>(p, grid, s)
+                          : launch_gemm2_inst<OUT_F32, ACT_NONE, BF16, false, 128>(p, grid, s);
     if (p.act == ACT_RELU) return launch_gemm2_inst<OUT_HALF, ACT_RELU, BF16, false, 128>(p, grid, s);
     return launch_gemm2_inst<OUT_HALF, ACT_NONE, BF16, false, 128>(p, grid, s);
   }
@@ -327,6 +330,15 @@ cudaError_t launch_gemm(const GemmParams& p, int bn, int grid, bool two_cta, cud
 }
 
 constexpr double kCostPair = 1.00, kCost256 = 1.08, kCost128 = 0.60;
+// 256 x 128 pair tiles (fp32-output GEMMs only: proj / fc2 at small M), cost per pair tile; DPT_COST_PAIR128 overrides
+double cost_pair128() {
+  static double v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_COST_PAIR128");
+    v = e ? atof(e) : 0.60;  // measured at B=4 / 8 (profiles/r2_pair128_f32.txt): on par with 128 x 128 single-CTA tiles
+  }
+  return v;
+}
 
 bool two_cta_enabled() {
   static int v = -1;
@@ -351,7 +363,7 @@ int gemm_mode() {
 // Tile choice for wide GEMMs (N > 128). Tiles are dealt round-robin to a persistent grid, so a launch costs
 // rounds x time-per-tile; the relative tile costs below were fitted to per-launch timings on B200.
 struct TileChoice { int bn; bool two_cta; };
-TileChoice choose_tile(long long m_tiles, int N, int num_sms) {
+TileChoice choose_tile(long long m_tiles, int N, int num_sms, bool f32_out) {
   const long long pairs = (m_tiles + 1) / 2;
   const int nt256 = (N + 255) / 256, nt128 = (N + 127) / 128;
   const bool pairs_ok = two_cta_enabled() && pairs * nt256 >= num_sms / 2;
@@ -365,6 +377,8 @@ TileChoice choose_tile(long long m_tiles, int N, int num_sms) {
   const double c_pair = pairs_ok ? rounds(pairs * nt256, num_sms / 2) * kCostPair : 1e30;
   const double c_256 = rounds(m_tiles * nt256, num_sms) * kCost256;
   const double c_128 = rounds(m_tiles * nt128, num_sms) * kCost128;
+  const double c_pair128 = (pairs_ok && f32_out) ? rounds(pairs * nt128, num_sms / 2) * cost_pair128() : 1e30;
+  if (c_pair128 < c_pair && c_pair128 < c_256 && c_pair128 < c_128) return {128, true};
   if (c_pair <= c_256 && c_pair <= c_128) return {256, true};
   return c_256 <= c_128 ? TileChoice{256, false} : TileChoice{128, false};
 }
@@ -436,7 +450,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
   int bn = op.out_kind == OUT_HEAD ? 32 : pick_block_n(op.N);
   bool two_cta = false;
   if (bn == 256 && op.out_kind != OUT_HEAD) {
-    const TileChoice tc = choose_tile(m_tiles_all, op.N, c.num_sms);
+    const TileChoice tc = choose_tile(m_tiles_all, op.N, c.num_sms, op.out_kind == OUT_F32);
     bn = tc.bn;
     two_cta = tc.two_cta;
   } else if (bn == 128 && op.taps == 9 && op.out_kind == OUT_HALF && op.act != ACT_GELU && two_cta_enabled() &&

@@ -94,7 +94,8 @@ struct __align__(64) GemmParams {
 template <int BLOCK_N, bool TWO_CTA = false, bool F32OUT = false>
 struct GemmCfg {
   static constexpr int STAGES_BASE = TWO_CTA ? (BLOCK_N == 256 ? 6 : 8) : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
-  static constexpr int STAGES = !F32OUT ? STAGES_BASE : (BLOCK_N == 64 ? 6 : (BLOCK_N == 32 ? 8 : STAGES_BASE - 1));
+  static constexpr int STAGES = !F32OUT ? STAGES_BASE
+                                : (BLOCK_N == 64 ? 6 : (BLOCK_N == 32 ? 8 : ((TWO_CTA && BLOCK_N == 128) ? STAGES_BASE - 2 : STAGES_BASE - 1)));
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = (TWO_CTA ? BLOCK_N / 2 : BLOCK_N) * GEMM_BLOCK_K * 2;
   static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP;

@@ -65,3 +65,33 @@ def test_allgather_depth_c_entry_two_ranks():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True, 0), (1, True, 0)], res
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_models_on_two_gpus_in_one_process():
+    """one process, one handle per device: kernels opt into their shared-memory size per DEVICE (not per process), and
+    every entry point runs on the handle's device whatever the caller's current device is"""
+    import tempfile
+
+    from muggled_dpt_b200 import make_dpt_from_state_dict
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict("vits", seed=11)
+    img = O.make_input(2, 252, 196, seed=9)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "depth_anything_v2_vits.pth")
+        torch.save(sd, path)
+        _, m0 = make_dpt_from_state_dict(path)
+        _, m1 = make_dpt_from_state_dict(path)
+    m0.to(device="cuda:0", dtype=torch.bfloat16)
+    m1.to(device="cuda:1", dtype=torch.bfloat16)
+    torch.cuda.set_device(0)  # current device stays 0 while the second model runs on device 1
+    with torch.inference_mode():
+        d1 = m1(img.to("cuda:1", torch.bfloat16))
+        d0 = m0(img.to("cuda:0", torch.bfloat16))
+        t1, g1 = m1.patch_embed(img.to("cuda:1", torch.bfloat16))
+        taps1 = m1.imgencoder(t1, g1)
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    assert d0.device.index == 0 and d1.device.index == 1 and taps1[0].device.index == 1
+    assert torch.equal(d0.cpu(), d1.cpu())

@@ -27,7 +27,10 @@ for a, b in [("bench_vitl_b32.json", f"{rnd}_bench_vitl_b32_504.json"), ("bench_
              ("bench_swinv2_large_384.json", f"{rnd}_bench_swinv2_large_384.json"), ("bench_prepost.json", f"{rnd}_bench_prepost.json"),
              ("launch_table_vitl_b32.csv", f"{rnd}_launch_table_vitl_b32_504.csv"), ("launch_table_vitb.csv", f"{rnd}_launch_table_vitb.csv"),
              ("launch_table_beit_large_384.csv", f"{rnd}_launch_table_beit_large_384.csv"),
-             ("launch_table_swinv2_large_384.csv", f"{rnd}_launch_table_swinv2_large_384.csv")]:
+             ("launch_table_swinv2_large_384.csv", f"{rnd}_launch_table_swinv2_large_384.csv"),
+             ("bench_reference_cpu.json", f"{rnd}_bench_reference_cpu_arm.json"),
+             ("bench_reference_gpu_eager.json", f"{rnd}_bench_reference_gpu_eager_vitl_b32.json"),
+             ("parity_report.json", f"{rnd}_parity_report_five_configs.json")]:
     copy(a, b)
 
 
@@ -70,10 +73,17 @@ WANT = [("duration_us", "gpu__time_duration.sum"), ("dram_read_MB", "dram__bytes
         ("dram_throughput_pct", "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
         ("sm_throughput_pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
         ("xu_pipe_pct", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+        ("fma_pipe_pct", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+        ("alu_pipe_pct", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+        ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        ("sm_clock_ghz", "sm__cycles_elapsed.avg.per_second"),
         ("l2_hit_pct", "lts__t_sector_hit_rate.pct"), ("regs", "launch__registers_per_thread"), ("grid", "launch__grid_size")]
 traffic = {}
 for tag, title in [("gemm", "the four encoder GEMM launches of block 10 (qkv, proj, fc1, fc2)"), ("attn", "one attention launch"),
-                   ("misc", "memory-bound kernels (row_stats, outnorm LayerNorm, bilinear resizes)")]:
+                   ("misc", "memory-bound kernels (row_stats, outnorm LayerNorm, bilinear resizes) and the head's halo convolution"),
+                   ("attn_beit", "BEiT-L B=16 384^2 bf16: one bias-attention launch (bias tile staged by TMA)"),
+                   ("swin", "SwinV2-L B=16 384^2 fp16: seven consecutive launches of the block loop (qkv GEMM with q/k "
+                            "normalise epilogue, window attention d=32, proj, post-norm kernels, fc1, fc2)")]:
     p = os.path.join(src, f"ncu_{tag}_raw.csv")
     if not os.path.exists(p):
         continue
@@ -83,7 +93,8 @@ for tag, title in [("gemm", "the four encoder GEMM launches of block 10 (qkv, pr
     cols = [(n, hdr.index(m)) for n, m in WANT if m in hdr]
     out = os.path.join(dst, f"{rnd}_ncu_full_{tag}_in_model.csv")
     with open(out, "w") as f:
-        f.write(f"# ncu --set full --clock-control none, ViT-L B=32 504^2 bf16, {title} inside one forward (bench.py --steps 1 --warmup 3)\n")
+        model_txt = "" if tag in ("attn_beit", "swin") else "ViT-L B=32 504^2 bf16, "
+        f.write(f"# ncu --set full --clock-control none, {model_txt}{title} inside one forward (bench.py --steps 1 --warmup 3, DPT_GRAPH=0)\n")
         f.write("kernel," + ",".join(n for n, _ in cols) + "\n")
         for r in rows:
             vals = []
