@@ -87,6 +87,16 @@ int dpt_forward(dpt_handle h, const void* img_bchw, void* depth_bhw, void* works
 int dpt_forward_host(dpt_handle h, const void* host_img_bchw, void* host_depth_bhw, void* dev_img, void* dev_depth,
                      void* workspace, size_t workspace_bytes, int B, int H, int W, void* stream);
 
+/* Asynchronous, pipelinable form of dpt_forward_host: enqueues the H2D copy on `copy_in_stream`, the forward on `stream`
+ * (after that copy) and the D2H copy on `copy_out_stream` (after the forward) and returns at once. Calls that alternate
+ * between two (dev_img, dev_depth) pairs overlap the copies of one step with the forward of the other: the library
+ * orders every reuse of a device buffer with events it owns (H2D into dev_img waits for the last forward that read it,
+ * a forward into dev_depth waits for the last D2H out of it). The caller synchronises `copy_out_stream` before reading
+ * host_depth, and does not touch host_img until then. Host buffers should be pinned. */
+int dpt_forward_host_async(dpt_handle h, const void* host_img, void* host_depth, void* dev_img, void* dev_depth,
+                           void* workspace, size_t workspace_bytes, int B, int H, int W, void* stream,
+                           void* copy_in_stream, void* copy_out_stream);
+
 /* pre / post-processing around the path ------------------------------------------ */
 /* PatchEmbed.prepare_image (v2_depthanything/patch_embed.py:103-145): uint8 BGR image [IH, IW, 3] (device) -> RGB,
  * antialiased bilinear resize to OH x OW (F.interpolate(mode="bilinear", antialias=True, align_corners=False)),

@@ -61,6 +61,7 @@ SYMBOLS = [
     ("dpt_workspace_bytes", _I, [_VP, _I, _I, _I, C.POINTER(_SZ)]),
     ("dpt_forward", _I, [_VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_forward_host", _I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP]),
+    ("dpt_forward_host_async", _I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP, _VP, _VP]),
     ("dpt_patch_embed", _I, [_VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_encoder", _I, [_VP, _VP, _PP4, _VP, _SZ, _I, _I, _I, _VP]),
     ("dpt_reassemble", _I, [_VP, _PP4, _PP4, _VP, _SZ, _I, _I, _I, _VP]),

@@ -57,6 +57,7 @@ struct Plan {
   bool init_done = false;
   cudaGraphExec_t graph_exec = nullptr;  // the replayed launches as one CUDA graph (built on the second use)
   int uses = 0;
+  unsigned long long last_used = 0;
   // cache key
   const void* img = nullptr;
   const void* out = nullptr;
@@ -96,7 +97,14 @@ struct dpt_model_s {
   std::unordered_map<std::string, Weight> weights;
   std::unordered_map<std::string, std::vector<float>> host_copies;  // "*_host" weights (tiny, read at plan time)
   std::string err;
-  Plan fwd_plan;
+  // launch plans of dpt_forward, one per (image buffer, depth buffer, workspace, shape) - a double-buffered host loop
+  // alternates between two of them; least recently used is replaced
+  static constexpr int kMaxPlans = 4;
+  Plan plans[kMaxPlans];
+  unsigned long long plan_clock = 0;
+  // dpt_forward_host_async: per device buffer, the event of its last reader / writer (see there)
+  struct BufEvent { const void* ptr = nullptr; cudaEvent_t ev = nullptr; bool armed = false; };
+  std::vector<BufEvent> img_read_done, depth_copied, h2d_done;
   int last_launches = 0;
   int num_sms = 148;
   int device = 0;
@@ -1656,7 +1664,7 @@ int build_and_run(dpt_model_s* h, void* ws, size_t ws_bytes, void* stream, Build
   if (guard.err != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err); return DPT_ERR_CUDA; }
   // a stage call lays its own tables / scratch out in the persistent end of the workspace: if the forward plan lives in
   // the same workspace its per-grid tables have to be rebuilt before its next use
-  h->fwd_plan.init_done = false;
+  for (Plan& pl : h->plans) pl.init_done = false;
   std::vector<LaunchFn> launches;
   Ctx c = make_ctx(h, ws, ws_bytes, &launches, false);
   if (!fn(c)) {
@@ -1709,8 +1717,12 @@ int dpt_create(const dpt_config* cfg, dpt_handle* out) {
 
 void dpt_destroy(dpt_handle h) {
   if (!h) return;
-  if (h->fwd_plan.graph_exec) cudaGraphExecDestroy(h->fwd_plan.graph_exec);
+  for (Plan& pl : h->plans)
+    if (pl.graph_exec) cudaGraphExecDestroy(pl.graph_exec);
   for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
+  for (auto* v : {&h->img_read_done, &h->depth_copied, &h->h2d_done})
+    for (auto& b : *v)
+      if (b.ev) cudaEventDestroy(b.ev);
   delete h;
 }
 
@@ -1759,7 +1771,7 @@ int dpt_set_weight(dpt_handle h, const char* name, const void* dev_ptr, const in
     w.ptr = v.data();
   }
   h->weights[name] = w;
-  h->fwd_plan.valid = false;  // (the next dpt_forward rebuilds the plan, its tables and its graph)
+  for (Plan& pl : h->plans) pl.valid = false;  // (the next dpt_forward rebuilds the plan, its tables and its graph)
   return DPT_OK;
 }
 
@@ -1821,8 +1833,23 @@ int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_
   if (!h || !img || !depth || !ws) return DPT_ERR_INVALID;
   DeviceGuard guard(h->device);
   if (guard.err != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err); return DPT_ERR_CUDA; }
-  Plan& pl = h->fwd_plan;
-  if (!(pl.valid && pl.img == img && pl.out == depth && pl.ws == ws && pl.B == B && pl.H == H && pl.W == W)) {
+  Plan* hit = nullptr;
+  Plan* victim = nullptr;  // an unused slot, else the least recently used plan
+  for (Plan& c : h->plans) {
+    if (c.valid && c.img == img && c.out == depth && c.ws == ws && c.B == B && c.H == H && c.W == W) hit = &c;
+    if (!c.valid) {
+      if (!victim || victim->valid) victim = &c;
+    } else if (!victim || (victim->valid && c.last_used < victim->last_used)) {
+      victim = &c;
+    }
+  }
+  Plan& pl = hit ? *hit : *victim;
+  pl.last_used = ++h->plan_clock;
+  if (!hit) {
+    // plans that share this workspace keep their per-grid tables in the same place with the same contents, but a plan
+    // for another shape in the same workspace would overwrite them: those rebuild their tables on their next use
+    for (Plan& c : h->plans)
+      if (&c != &pl && c.valid && c.ws == ws && !(c.B == B && c.H == H && c.W == W)) c.init_done = false;
     pl.valid = false;
     pl.launches.clear();
     pl.init.clear();
@@ -1886,6 +1913,51 @@ int dpt_forward_host(dpt_handle h, const void* host_img, void* host_depth, void*
   if (e != cudaSuccess) { h->err = std::string("D2H copy: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { h->err = std::string("stream sync: ") + cudaGetErrorString(e); return DPT_ERR_CUDA; }
+  return DPT_OK;
+}
+
+// event attached to a device buffer (created on first use); `armed` = it has been recorded at least once
+static cudaEvent_t buf_event(std::vector<dpt_model_s::BufEvent>& v, const void* ptr, bool** armed) {
+  for (auto& b : v)
+    if (b.ptr == ptr) { *armed = &b.armed; return b.ev; }
+  dpt_model_s::BufEvent b;
+  b.ptr = ptr;
+  if (cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  v.push_back(b);
+  *armed = &v.back().armed;
+  return v.back().ev;
+}
+
+int dpt_forward_host_async(dpt_handle h, const void* host_img, void* host_depth, void* dev_img, void* dev_depth, void* ws,
+                           size_t ws_bytes, int B, int H, int W, void* stream, void* copy_in_stream, void* copy_out_stream) {
+  if (!h || !host_img || !host_depth || !dev_img || !dev_depth || !copy_in_stream || !copy_out_stream) return DPT_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (guard.err != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err); return DPT_ERR_CUDA; }
+  cudaStream_t s = (cudaStream_t)stream, s_in = (cudaStream_t)copy_in_stream, s_out = (cudaStream_t)copy_out_stream;
+  bool *a_read = nullptr, *a_copied = nullptr, *a_h2d = nullptr;
+  cudaEvent_t ev_read = buf_event(h->img_read_done, dev_img, &a_read);      // last forward that READ dev_img is done
+  cudaEvent_t ev_copied = buf_event(h->depth_copied, dev_depth, &a_copied);  // last D2H that read dev_depth is done
+  cudaEvent_t ev_h2d = buf_event(h->h2d_done, dev_img, &a_h2d);              // this call's H2D into dev_img is done
+  if (!ev_read || !ev_copied || !ev_h2d) { h->err = "cudaEventCreate failed"; return DPT_ERR_CUDA; }
+  auto fail = [&](const char* what, cudaError_t e) { h->err = std::string(what) + ": " + cudaGetErrorString(e); return DPT_ERR_CUDA; };
+  cudaError_t e;
+  // 1. H2D on the copy-in stream, once the previous forward that read this image buffer has finished with it
+  if (*a_read && (e = cudaStreamWaitEvent(s_in, ev_read, 0)) != cudaSuccess) return fail("cudaStreamWaitEvent", e);
+  if ((e = cudaMemcpyAsync(dev_img, host_img, (size_t)B * 3 * H * W * 2, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return fail("H2D copy", e);
+  if ((e = cudaEventRecord(ev_h2d, s_in)) != cudaSuccess) return fail("cudaEventRecord", e);
+  *a_h2d = true;
+  // 2. forward on the compute stream, after that copy and after the previous D2H out of this depth buffer
+  if ((e = cudaStreamWaitEvent(s, ev_h2d, 0)) != cudaSuccess) return fail("cudaStreamWaitEvent", e);
+  if (*a_copied && (e = cudaStreamWaitEvent(s, ev_copied, 0)) != cudaSuccess) return fail("cudaStreamWaitEvent", e);
+  const int rc = dpt_forward(h, dev_img, dev_depth, ws, ws_bytes, B, H, W, stream);
+  if (rc != DPT_OK) return rc;
+  if ((e = cudaEventRecord(ev_read, s)) != cudaSuccess) return fail("cudaEventRecord", e);
+  *a_read = true;
+  // 3. D2H on the copy-out stream, after the forward
+  if ((e = cudaStreamWaitEvent(s_out, ev_read, 0)) != cudaSuccess) return fail("cudaStreamWaitEvent", e);
+  if ((e = cudaMemcpyAsync(host_depth, dev_depth, (size_t)B * H * W * 2, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return fail("D2H copy", e);
+  if ((e = cudaEventRecord(ev_copied, s_out)) != cudaSuccess) return fail("cudaEventRecord", e);
+  *a_copied = true;
   return DPT_OK;
 }
 

@@ -238,7 +238,7 @@ class DPTModel(torch.nn.Module):
                 else:  # "host": tiny fp32 vectors the library copies into the handle
                     d, code = t.to(dtype=torch.float32).contiguous(), N.DPT_F32
                 set_weight(name, d, code)
-        self._workspace, self._ws_key, self._io = None, None, {}
+        self._workspace, self._ws_key, self._io, self._io_extra, self._copy_streams = None, None, {}, None, None
 
     def _release(self):
         if self._handle is not None:
@@ -292,14 +292,7 @@ class DPTModel(torch.nn.Module):
     def forward(self, image_rgb_normalized_bchw: torch.Tensor) -> torch.Tensor:
         """DPTModel.forward (dpt_model.py:61-83): BxCxHxW -> BxHxW inverse depth, in the model dtype."""
         B, H, W = self._check_image(image_rgb_normalized_bchw)
-        io = self._io.get((B, H, W))
-        if io is None:
-            io = (
-                torch.empty((B, 3, H, W), dtype=self._dtype, device=self._device),
-                torch.empty((B, H, W), dtype=self._dtype, device=self._device),
-            )
-            self._io = {(B, H, W): io}
-        img, out = io
+        img, out = self._io_buffers(B, H, W)
         img.copy_(image_rgb_normalized_bchw)  # fixed buffers keep the recorded launch plan valid across calls
         self.forward_into(img, out)
         return out.clone()
@@ -315,8 +308,7 @@ class DPTModel(torch.nn.Module):
         N.check(rc, self._handle, "dpt_forward")
         return out
 
-    def forward_host(self, host_img: torch.Tensor, host_out: torch.Tensor) -> torch.Tensor:
-        """Host buffers in/out through dpt_forward_host (H2D + forward + D2H + sync)."""
+    def _check_host_buffers(self, host_img: torch.Tensor, host_out: torch.Tensor):
         device, dtype = self._require_ready()
         for name, t in (("host_img", host_img), ("host_out", host_out)):
             if not isinstance(t, torch.Tensor) or t.device.type != "cpu":
@@ -331,13 +323,31 @@ class DPTModel(torch.nn.Module):
         self._check_size(H, W)
         if tuple(host_out.shape) != (B, H, W):
             raise ValueError(f"forward_host: host_out must have shape {(B, H, W)}, got {tuple(host_out.shape)}")
-        io = self._io.get((B, H, W))
-        if io is None:
-            io = (
+        return B, H, W
+
+    def _io_buffers(self, B: int, H: int, W: int, slot: int = 0):
+        """device-side (image, depth) pair `slot` for host-buffer forwards of this shape"""
+        key = (B, H, W)
+        if key not in self._io:
+            self._io = {key: (
                 torch.empty((B, 3, H, W), dtype=self._dtype, device=self._device),
                 torch.empty((B, H, W), dtype=self._dtype, device=self._device),
-            )
-            self._io = {(B, H, W): io}
+            )}
+            self._io_extra = {}
+        if slot == 0:
+            return self._io[key]
+        extra = getattr(self, "_io_extra", None)
+        if extra is None or extra.get("key") != key:
+            extra = self._io_extra = {"key": key}
+        if slot not in extra:
+            extra[slot] = (torch.empty((B, 3, H, W), dtype=self._dtype, device=self._device),
+                           torch.empty((B, H, W), dtype=self._dtype, device=self._device))
+        return extra[slot]
+
+    def forward_host(self, host_img: torch.Tensor, host_out: torch.Tensor) -> torch.Tensor:
+        """Host buffers in/out through dpt_forward_host (H2D + forward + D2H + sync)."""
+        B, H, W = self._check_host_buffers(host_img, host_out)
+        io = self._io_buffers(B, H, W)
         ws = self._get_workspace(B, H, W)
         with torch.cuda.device(self._device):
             rc = N.lib().dpt_forward_host(self._handle, C.c_void_p(host_img.data_ptr()), C.c_void_p(host_out.data_ptr()),
@@ -345,6 +355,27 @@ class DPTModel(torch.nn.Module):
                                           C.c_void_p(ws.data_ptr()), ws.numel(), B, H, W, self._stream())
         N.check(rc, self._handle, "dpt_forward_host")
         return host_out
+
+    def forward_host_async(self, host_img: torch.Tensor, host_out: torch.Tensor, slot: int = 0) -> torch.cuda.Event:
+        """Pipelinable host-buffer forward (dpt_forward_host_async): H2D on a copy-in stream, forward on the current
+        stream, D2H on a copy-out stream; returns an event to `.synchronize()` on before reading `host_out`. Alternate
+        `slot` between 0 and 1 (each slot owns a device image / depth pair) and the copies of one step overlap the
+        forward of the other. The caller must not touch `host_img` / `host_out` until the returned event completes."""
+        B, H, W = self._check_host_buffers(host_img, host_out)
+        io = self._io_buffers(B, H, W, slot)
+        ws = self._get_workspace(B, H, W)
+        with torch.cuda.device(self._device):
+            if getattr(self, "_copy_streams", None) is None:
+                self._copy_streams = (torch.cuda.Stream(self._device), torch.cuda.Stream(self._device))
+            s_in, s_out = self._copy_streams
+            rc = N.lib().dpt_forward_host_async(self._handle, C.c_void_p(host_img.data_ptr()), C.c_void_p(host_out.data_ptr()),
+                                                C.c_void_p(io[0].data_ptr()), C.c_void_p(io[1].data_ptr()),
+                                                C.c_void_p(ws.data_ptr()), ws.numel(), B, H, W, self._stream(),
+                                                C.c_void_p(s_in.cuda_stream), C.c_void_p(s_out.cuda_stream))
+            N.check(rc, self._handle, "dpt_forward_host_async")
+            done = torch.cuda.Event()
+            done.record(s_out)
+        return done
 
     def last_launch_count(self) -> int:
         return int(N.lib().dpt_last_launch_count(self._handle))

@@ -380,3 +380,32 @@ def test_swinv2_tiny_256_against_oracle():
     assert tuple(depth.shape) == (2, 256, 256)
     gate("swin.tiny256.fp16.depth.rel_l2", e[0], 0.03)  # clamp-reaching logit scales, see the note in the micro test
     gate("swin.tiny256.fp16.depth.max_rel", e[2], 0.06)
+
+
+def test_pipelined_host_forward_matches_synchronous_one():
+    """dpt_forward_host_async on two alternating device buffer pairs (copies overlap the other slot's forward): every
+    step's result equals the synchronous dpt_forward_host result of the same input, bit for bit"""
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict("vits", seed=11)
+    cfg, model = _load_model(sd, torch.bfloat16)
+    B, H, W = 2, 252, 196
+    imgs = [O.make_input(B, H, W, seed=40 + i).to(torch.bfloat16).pin_memory() for i in range(6)]
+    sync_out = []
+    for x in imgs:
+        o = torch.empty(B, H, W, dtype=torch.bfloat16).pin_memory()
+        model.forward_host(x, o)
+        sync_out.append(o.clone())
+    outs = [torch.empty(B, H, W, dtype=torch.bfloat16).pin_memory() for _ in imgs]
+    pending = [None, None]
+    for i, x in enumerate(imgs):
+        k = i & 1
+        if pending[k] is not None:
+            pending[k].synchronize()
+        pending[k] = model.forward_host_async(x, outs[i], slot=k)
+    for ev in pending:
+        ev.synchronize()
+    for i in range(len(imgs)):
+        assert torch.equal(outs[i], sync_out[i]), i
+    with pytest.raises(ValueError):
+        model.forward_host_async(imgs[0], torch.empty(B, H, W + 1, dtype=torch.bfloat16))
