@@ -407,6 +407,7 @@ struct GemmOp {
   long long ldo = 0;                  // default N
   int OH = 0, OW = 0, so = 1, oy = 0, ox = 0;  // default OH = H, OW = W
   int shuffle_n = 0;                  // merged ConvTranspose: N = so*so*shuffle_n (gemm_tc.cuh)
+  int force_bn = 0;                   // 0 = tile width chosen by the cost model; else single-CTA tiles of this width
   const void* add1 = nullptr;
   long long ld_add1 = 0;
   const void* add2 = nullptr;
@@ -457,7 +458,9 @@ bool add_gemm(Ctx& c, GemmOp op) {
   const long long m_tiles_all = (long long)op.B * ((op.W + TW - 1) / TW) * ((op.H + TH - 1) / TH);
   int bn = op.out_kind == OUT_HEAD ? 32 : pick_block_n(op.N);
   bool two_cta = false;
-  if (bn == 256 && op.out_kind != OUT_HEAD) {
+  if (op.force_bn > 0) {
+    bn = op.force_bn;
+  } else if (bn == 256 && op.out_kind != OUT_HEAD) {
     const TileChoice tc = choose_tile(m_tiles_all, op.N, c.num_sms, op.out_kind == OUT_F32);
     bn = tc.bn;
     two_cta = tc.two_cta;
@@ -1363,14 +1366,18 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
       res = c.ar.alloc((size_t)B * rh * rw * R * 2);
       const long long rows_per_sub = uw->shape[0] / (s * s);
       const int kpad = (int)uw->shape[1];
-      // one launch when the channel count is a whole number of n-tiles (the tile then lies inside one sub-pixel block)
-      const int bn_merged = (s * s * R) > 128 ? 256 : pick_block_n(s * s * R);
-      if (R % bn_merged == 0 && R % 128 == 0) {
+      // one launch when the channel count is a whole number of n-tiles (the tile then lies inside one sub-pixel block):
+      // the cost model's choice for multiples of 256 / 128 channels, else the widest tile that divides R (ViT-B: 96 -> 32,
+      // 192 -> 64; ViT-S: 48 -> s*s launches)
+      int bn_forced = 0;  // multiples of 256: any tile width the cost model picks divides R
+      if (R % 256 != 0) bn_forced = R % 128 == 0 ? 128 : (R % 64 == 0 ? 64 : (R % 32 == 0 ? 32 : -1));
+      if (bn_forced >= 0) {
         GemmOp op;
         op.A = proj; op.B = B; op.Ht = gh; op.Wt = gw; op.C = R;
         op.Wt_ptr = uw->ptr; op.N = s * s * R; op.kpad = kpad; op.ldo = R;
         op.bias = (const float*)ub->ptr; op.out = res;
         op.so = s; op.shuffle_n = R; op.OH = rh; op.OW = rw; op.label = "convT";
+        op.force_bn = bn_forced;
         add_gemm(c, op);
       } else
       for (int sub = 0; sub < s * s; ++sub) {
