@@ -251,7 +251,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_reference_gpu(args, rank, world):
@@ -266,7 +266,7 @@ def run_reference_gpu(args, rank, world):
     assert torch.cuda.is_available()
     fwd, kind, model = load_reference_model(args.model)
     if model is None:
-        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref is absent (run oracle/build_ref.py where /root/reference exists)"}))
+        emit({"impl": "reference-gpu", "unavailable": "oracle/_ref is absent (run oracle/build_ref.py where /root/reference exists)"})
         return
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     dev = torch.device("cuda", 0)
@@ -299,11 +299,31 @@ def run_reference_gpu(args, rank, world):
         "reference_run": {"device": "cuda:0 (stock PyTorch eager: cuBLAS / cuDNN / fused SDPA)", "compute_dtype": args.dtype,
                           "memory_format": "channels_last", "kind": kind, "output_shape": list(out.shape)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, for one) print to fd 1: point it at stderr for the run and keep the original for
+    the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse_args()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -542,7 +562,7 @@ def main():
             tf = gf * 1e9 * fps / 1e12
             line["model_tflops"] = {"algorithmic_gflop_per_frame": gf, "achieved_tflops_whole_job": tf,
                                     "frac_of_sustained_peak_per_gpu": tf / world / peaks["tflops_sustained"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     if world > 1:
         if native_gather is not None:
