@@ -56,6 +56,7 @@ struct Plan {
   std::vector<LaunchFn> init;
   bool init_done = false;
   cudaGraphExec_t graph_exec = nullptr;  // the replayed launches as one CUDA graph (built on the second use)
+  bool graph_tried = false;
   int uses = 0;
   unsigned long long last_used = 0;
   // cache key
@@ -1862,6 +1863,7 @@ int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_
     pl.init.clear();
     pl.init_done = false;
     pl.uses = 0;
+    pl.graph_tried = false;
     destroy_plan_graph(pl);
     Ctx c = make_ctx(h, ws, ws_bytes, &pl.launches, false);
     c.init = &pl.init;
@@ -1892,7 +1894,10 @@ int dpt_forward(dpt_handle h, const void* img, void* depth, void* ws, size_t ws_
   // first use: launch by launch (this also opts every kernel into its shared-memory size on this device); second use:
   // capture; afterwards: one cudaGraphLaunch per forward. Per-launch profiling needs the launch-by-launch path.
   if (graph_enabled() && !h->profiling && pl.uses >= 2) {
-    if (!pl.graph_exec && pl.uses == 2) capture_plan_graph(h, pl);
+    if (!pl.graph_exec && !pl.graph_tried) {
+      pl.graph_tried = true;
+      capture_plan_graph(h, pl);
+    }
     if (pl.graph_exec) {
       const cudaError_t e = cudaGraphLaunch(pl.graph_exec, s);
       if (e != cudaSuccess) {
