@@ -76,3 +76,35 @@ def test_swinv2_micro_shapes(shape):
         out = model(img.to("cuda", torch.float16))
     assert tuple(out.shape) == tuple(shape)
     gate("fuzz.swinv2_micro.fp16.%dx%dx%d.rel_l2" % shape, _rel(out, ref), 6e-3)
+
+
+def test_large_images_many_kv_steps():
+    """far more tokens than the benchmark sizes: ViT-S at 1008 x 756 (3889 tokens, 61 kv steps per q tile, 31 q tiles),
+    a BEiT-shaped model at 512 x 512 (1025 tokens with bias tables resized 4x) and a SwinV2-shaped one at 512 x 384"""
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict("vits", seed=11)
+    img = O.make_input(1, 1008, 756, seed=12)
+    ref = O.forward(sd, img)
+    model = _load(sd, "depth_anything_v2_vits.pth", torch.float16)
+    with torch.inference_mode():
+        out = model(img.to("cuda", torch.float16))
+    gate("fuzz.vits.fp16.1x1008x756.rel_l2", _rel(out, ref), 3e-3)
+    del model
+
+    sd = O.make_synthetic_state_dict_beit("beit_tiny", seed=5)
+    img = O.make_input(1, 512, 512, seed=13)
+    ref = O.forward_beit(sd, img)
+    model = _load(sd, "dpt_beit_tiny.pt", torch.float16)
+    with torch.inference_mode():
+        out = model(img.to("cuda", torch.float16))
+    gate("fuzz.beit_tiny.fp16.1x512x512.rel_l2", _rel(out, ref), 4e-3)
+    del model
+
+    sd = O.make_synthetic_state_dict_swinv2("swinv2_micro", seed=21, logit_std=0.3)
+    img = O.make_input(1, 512, 384, seed=14)
+    ref = O.forward_swinv2(sd, img)
+    model = _load(sd, "dpt_swin2_micro.pt", torch.float16)
+    with torch.inference_mode():
+        out = model(img.to("cuda", torch.float16))
+    gate("fuzz.swinv2_micro.fp16.1x512x384.rel_l2", _rel(out, ref), 6e-3)
