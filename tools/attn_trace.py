@@ -1,10 +1,14 @@
 #!/usr/bin/env python3
-"""Per-phase clock64 timeline of the attention softmax warps (trace build of the library, -DATT_TRACE).
+"""Per-phase clock64 timeline of the softmax warps of the FIRST-GENERATION attention kernel (attn_tc.cuh, selected with
+DPT_ATTN_V1=1; trace build of the library, -DATT_TRACE). The stamps are invasive (global stores per phase): use the
+relative phase lengths, not the absolute step time. The shipped kernel (attn64_tc.cuh) is profiled with ncu instead.
 usage (GPU box): python tools/attn_trace.py [B]     builds muggled_dpt_b200/lib/libdpt_b200_trace.so first"""
 import ctypes
 import os
 import subprocess
 import sys
+
+os.environ["DPT_ATTN_V1"] = "1"
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
