@@ -1,7 +1,7 @@
 """-m gpu: the reference's own example scripts (simple_examples/depth_prediction.py and internal_features.py) run
 against the product with ONLY the import swapped (`muggled_dpt.make_dpt` -> `muggled_dpt_b200.make_dpt`) and the two
-path constants filled in. The scripts are the unmodified files oracle/build_ref.py placed under oracle/_ref (they travel
-to the GPU box with the snapshot); nothing here reads /root/reference."""
+path constants filled in. The scripts are the unmodified files oracle/build_ref.py archived under oracle/_ref (the archive
+travels to the GPU box with the snapshot); nothing here reads /root/reference."""
 import os
 import re
 import subprocess
@@ -15,16 +15,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXAMPLES = os.path.join(ROOT, "oracle", "_ref", "simple_examples")
 
 
 def _run_example(script_name, sd, ckpt_name, image_hw):
     import cv2
 
-    src_path = os.path.join(EXAMPLES, script_name)
-    if not os.path.exists(src_path):
-        pytest.skip("oracle/_ref/simple_examples is absent (run oracle/build_ref.py where /root/reference exists)")
-    text = open(src_path).read()
+    from oracle.build_ref import read_example, ref_available
+
+    if not ref_available():
+        pytest.skip("oracle/_ref is absent (run oracle/build_ref.py where /root/reference exists)")
+    text = read_example(script_name)
     assert text.count("from muggled_dpt.make_dpt import make_dpt_from_state_dict") == 1
     with tempfile.TemporaryDirectory() as td:
         rng = np.random.default_rng(3)
