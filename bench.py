@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-gpu"])
     ap.add_argument("--ref-frames-per-step", type=int, default=1, help="reference arm: frames per timed step (bounded sample)")
     ap.add_argument("--model", default="vitl",
-                    choices=["vitl", "vitb", "vits", "tiny", "beit_large_384", "beit_base_384", "beit_tiny",
+                    choices=["vitl", "vitb", "vits", "vitg", "tiny", "beit_large_384", "beit_base_384", "beit_tiny",
                              "swinv2_large_384", "swinv2_base_384", "swinv2_tiny_256", "swinv2_micro"])
     ap.add_argument("--batch", type=int, default=32, help="global batch (frames per step)")
     ap.add_argument("--size", type=int, default=504)
@@ -138,7 +138,8 @@ def _oracle_model(O, model_name):
         return O.make_synthetic_state_dict_beit(model_name, seed=11), O.forward_beit
     if model_name.startswith("swinv2"):
         return O.make_synthetic_state_dict_swinv2(model_name, seed=11), O.forward_swinv2
-    return O.make_synthetic_state_dict(model_name, seed=11), O.forward
+    sd = O.make_synthetic_state_dict(model_name, seed=11)
+    return (O.giantify(sd, seed=11) if model_name == "vitg" else sd), O.forward
 
 
 def _checkpoint_file_name(model_name):

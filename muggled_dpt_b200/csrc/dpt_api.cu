@@ -309,6 +309,7 @@ cudaError_t launch_gemm2_dt(const GemmParams& p, int bn, int grid, cudaStream_t 
                         : launch_gemm2_inst<OUT_F32, ACT_NONE, BF16>(p, grid, s);
   if (p.act == ACT_GELU) return launch_gemm2_inst<OUT_HALF, ACT_GELU, BF16>(p, grid, s);
   if (p.act == ACT_RELU) return launch_gemm2_inst<OUT_HALF, ACT_RELU, BF16>(p, grid, s);
+  if (p.act == ACT_SWIGLU) return launch_gemm2_inst<OUT_HALF, ACT_SWIGLU, BF16>(p, grid, s);
   return launch_gemm2_inst<OUT_HALF, ACT_NONE, BF16>(p, grid, s);
 }
 
@@ -319,6 +320,9 @@ cudaError_t launch_gemm_bn(const GemmParams& p, int grid, cudaStream_t s) {
                         : launch_gemm_inst<BN, OUT_F32, ACT_NONE, BF16>(p, grid, s);
   if (p.act == ACT_GELU) return launch_gemm_inst<BN, OUT_HALF, ACT_GELU, BF16>(p, grid, s);
   if (p.act == ACT_RELU) return launch_gemm_inst<BN, OUT_HALF, ACT_RELU, BF16>(p, grid, s);
+  if constexpr (BN >= 128) {
+    if (p.act == ACT_SWIGLU) return launch_gemm_inst<BN, OUT_HALF, ACT_SWIGLU, BF16>(p, grid, s);
+  }
   return launch_gemm_inst<BN, OUT_HALF, ACT_NONE, BF16>(p, grid, s);
 }
 
@@ -436,12 +440,17 @@ bool add_gemm(Ctx& c, GemmOp op) {
   if (op.W == 0) op.W = op.Wt - op.xoff;
   if (op.OH == 0) op.OH = op.H * op.so;
   if (op.OW == 0) op.OW = op.W * op.so;
-  if (op.ldo == 0) op.ldo = op.N;
+  if (op.ldo == 0) op.ldo = op.act == ACT_SWIGLU ? op.N / 2 : op.N;
   if (op.kpad == 0) op.kpad = (op.C + 63) / 64 * 64;
   if (op.C % 8 != 0) return c.fail("gemm: channel count must be a multiple of 8");
   if (op.out_kind != OUT_HEAD && op.N % 8 != 0) return c.fail("gemm: N must be a multiple of 8");
   if (op.out_kind == OUT_F32 && op.act != ACT_NONE) return c.fail("gemm: fp32 output has no activation variant");
   if (op.act == ACT_SIGMOID) return c.fail("gemm: sigmoid is only available in head mode");
+  if (op.act == ACT_SWIGLU) {  // output = N / 2 columns; tiles of 128 or 256 GEMM columns (gemm_tc.cuh)
+    if (op.N % 128 != 0 || op.out_kind != OUT_HALF || op.shuffle_n > 0 || op.add1 || op.add2 || op.out2_relu || op.force_bn)
+      return c.fail("gemm: the SwiGLU epilogue needs N % 128 == 0, a 16-bit output and no residual / shuffle");
+    if (op.ldo == 0) op.ldo = op.N / 2;
+  }
   if (c.dry) return true;
 
   GemmParams p;
@@ -897,12 +906,6 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
   void* qkv = c.ar.alloc((size_t)M * 3 * F * 2);
   void* att = c.ar.alloc((size_t)M * F * 2);
   void* hid = c.ar.alloc((size_t)M * 4 * F * 2);
-  void* inner = nullptr;  // ViT-G: output of the doubled inner Linear of the SwiGLU FFN [M, 2h]
-  if (cfg.mlp_swiglu) {
-    const Weight* w0 = get_w(c, "blk0.fc1.w", hd);
-    if (!w0) return false;
-    inner = c.ar.alloc((size_t)M * (size_t)w0->shape[0] * 2);
-  }
 
   const bool is_beit = cfg.variant == DPT_VARIANT_BEIT;
   const Weight *on_w = nullptr, *on_b = nullptr;
@@ -964,10 +967,14 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
     const Weight *f1w = get_w(c, pre + "fc1.w", hd), *f1b = get_w(c, pre + "fc1.b", DPT_F32);
     const Weight *f2w = get_w(c, pre + "fc2.w", hd), *f2b = get_w(c, pre + "fc2.b", DPT_F32);
     if (!c.ok) return false;
-    // ViT-G: fc1 is the doubled inner Linear of the SwiGLU FFN [2h, F], fc2 the outer Linear [F, h] (K padded to 64)
+    // ViT-G: fc1 is the doubled inner Linear of the SwiGLU FFN packed [2 hp, F] - hp = h rounded up to 64, rows in
+    // blocks of 32 gate rows + the 32 linear rows of the same features, zero rows beyond h - and the gate is applied in
+    // fc1's epilogue (ACT_SWIGLU); fc2 is the outer Linear [F, hp]
     const bool swiglu = cfg.mlp_swiglu != 0;
-    const int hidden = swiglu ? (int)f1w->shape[0] / 2 : (int)f1w->shape[0];
-    if (swiglu && hidden % 8 != 0) return c.fail("SwiGLU: the hidden width must be a multiple of 8");
+    const int hidden_pad = (int)f2w->shape[1];  // fc2's K, a multiple of 64
+    const int hidden = swiglu ? hidden_pad : (int)f1w->shape[0];
+    if (swiglu && ((int)f1w->shape[0] != 2 * hidden_pad || hidden_pad > 4 * F))
+      return c.fail("SwiGLU: fc1 must be packed as [2 x padded hidden, F] with the padded hidden width <= 4 F");
     c.scope = pre;
     {
       GemmOp op;  // qkv = LN1(x) Wqkv^T + b
@@ -1009,22 +1016,9 @@ bool build_encoder(Ctx& c, const void* tokens, void* const taps[4], int B, int g
       GemmOp op;  // hid = GELU(LN2(x) W1^T + b1)
       op.A = ln; op.Wt = (int)M; op.C = F; op.Wt_ptr = f1w->ptr; op.N = swiglu ? 2 * hidden : hidden;
       op.kpad = (int)f1w->shape[1];
-      op.bias = (const float*)f1b->ptr; op.act = swiglu ? ACT_NONE : ACT_GELU; op.out = swiglu ? inner : hid; op.label = "fc1";
+      op.bias = (const float*)f1b->ptr; op.act = swiglu ? ACT_SWIGLU : ACT_GELU; op.out = hid; op.label = "fc1";
       op.ln_stats = stats; op.ln_parts = stats_parts; op.ln_colsum = (const float*)f1s->ptr; op.ln_eps = cfg.ln_eps;
       add_gemm(c, op);
-    }
-    const int hidden_pad = (int)f2w->shape[1];  // fc2's K, a multiple of 64
-    if (swiglu && !c.dry) {
-      // gate: hid[m, j] = silu(inner[m, j]) * inner[m, h + j]
-      if (hidden_pad > 4 * F) return c.fail("SwiGLU: hidden width exceeds the block buffers");
-      const int is_bf16 = c.is_bf16, nsm = c.num_sms;
-      c.add("swiglu:" + pre, 0.0, (double)M * 3.0 * hidden * 2.0, [=](cudaStream_t s) {
-        const int grid = ew_grid(M * (hidden_pad / 8), 256, nsm);
-        cudaError_t e;
-        DISPATCH_T(is_bf16, (e = launch_ex(swiglu_kernel<T>, dim3(grid), dim3(256), 0, s, false, (const T*)inner, (T*)hid, M,
-                                           hidden, hidden_pad)));
-        return e;
-      });
     }
     {
       GemmOp op;

@@ -33,7 +33,10 @@ constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_STAGE_BYTES_PER_WARP = 4096;  // 32 rows x 128 B
 
-enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+// ACT_SWIGLU (16-bit outputs, BLOCK_N >= 128): the GEMM columns come in blocks of 64 = 32 gate columns followed by the 32
+// linear columns of the same features (the packer interleaves the rows of the doubled Linear that way); the epilogue
+// writes silu(gate) * linear, so the output has N / 2 columns and the [M, N] intermediate never exists.
+enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3, ACT_SWIGLU = 4 };
 enum : int { OUT_HALF = 0, OUT_F32 = 1, OUT_HEAD = 2 };
 
 struct __align__(64) GemmParams {
@@ -423,9 +426,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           constexpr bool F32OUT = OUT_KIND == OUT_F32;
           constexpr int COLS_PER_STG = F32OUT ? 32 : 64;  // staging row = 128 B
           constexpr int ELEMS_PER_CHUNK = F32OUT ? 4 : 8;
-          constexpr int NCOLS_HERE = COLS_PER_STG < COLS_PER_WG ? COLS_PER_STG : COLS_PER_WG;
+          constexpr bool SWI = ACT == ACT_SWIGLU;             // two 32-column units -> 32 output columns
+          static_assert(!SWI || (!F32OUT && COLS_PER_WG >= 64), "SwiGLU epilogue: 16-bit output, BLOCK_N >= 128");
+          constexpr int OUT_COLS_PER_WG = SWI ? COLS_PER_WG / 2 : COLS_PER_WG;
+          constexpr int NCOLS_HERE = COLS_PER_STG < OUT_COLS_PER_WG ? COLS_PER_STG : OUT_COLS_PER_WG;
           constexpr int UNITS = COLS_PER_WG / 32;             // 32-column TMEM loads per tile and warp
-          constexpr int UNITS_PER_STG = NCOLS_HERE / 32;      // 1 (fp32 out) or 2 (16-bit out)
+          constexpr int UNITS_PER_STG = (NCOLS_HERE / 32) * (SWI ? 2 : 1);  // 1 (fp32 out), 2 (16-bit out), 2 or 4 (SwiGLU)
+          uint32_t gate[SWI ? 16 : 1];                        // silu(gate unit), packed 16-bit, until its linear unit arrives
           const int sub = lane & 7;  // 16-byte chunk within a 128-byte row segment (phase 2)
           // software pipeline: the TMEM load of unit u+1 is in flight while unit u is processed / stored
           // (OUT_F32 keeps a prefetched residual instead of a prefetched accumulator unit: registers)
@@ -450,14 +457,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if constexpr (!F32OUT) {
               if (u + 1 < UNITS) tmem_ld32(t_acc + (u + 1) * 32, vbuf[(u + 1) & 1]);
             }
-            const int c0 = (u / UNITS_PER_STG) * COLS_PER_STG;   // first column of this staging chunk
-            const int cc = (u % UNITS_PER_STG) * 32;             // column offset inside the staging chunk
+            const int c0 = (u / UNITS_PER_STG) * COLS_PER_STG;   // first (output) column of this staging chunk
+            const int cc = ((u % UNITS_PER_STG) >> (SWI ? 1 : 0)) * 32;  // column offset inside the staging chunk
+            const int gc = col_base + u * 32;                    // first GEMM column of this unit within the tile
             // ---- phase 1: my row, 32 columns: +bias, activation -> swizzled staging
             {
-              const float4* b4 = reinterpret_cast<const float4*>(bs + col_base + c0 + cc);
+              const float4* b4 = reinterpret_cast<const float4*>(bs + gc);
               float f[32];
               if (p.ln_stats != nullptr) {
-                const float4* s4 = reinterpret_cast<const float4*>(cs + col_base + c0 + cc);
+                const float4* s4 = reinterpret_cast<const float4*>(cs + gc);
                 const float2 rs2 = make_float2(ln_rstd, ln_rstd), rm2 = make_float2(ln_rm, ln_rm);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {  // packed fp32x2 FMAs: acc * rstd + (rm * colsum + bias)
@@ -484,7 +492,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               }
               if constexpr (ACT == ACT_NONE && !F32OUT) {
                 if (p.qk_logit != nullptr) {
-                  const int gcol = n_blk * BLOCK_N + col_base + c0 + cc;  // a multiple of 32 = one head
+                  const int gcol = n_blk * BLOCK_N + gc;  // a multiple of 32 = one head
                   if (gcol < 2 * p.qk_features) {
                     float ss = 0.0f;
 #pragma unroll
@@ -506,6 +514,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               } else if constexpr (ACT == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+              } else if constexpr (SWI) {
+                if ((u & 1) == 0) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    gate[j] = pack2(f[2 * j] * rcp_approx(1.0f + __expf(-f[2 * j])),
+                                    f[2 * j + 1] * rcp_approx(1.0f + __expf(-f[2 * j + 1])), is_bf16);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float2 g = unpack2(gate[j], is_bf16);
+                    f[2 * j] *= g.x;
+                    f[2 * j + 1] *= g.y;
+                  }
+                }
+              }
+              if constexpr (SWI) {
+                if ((u & 1) == 0) continue;  // the gate half: nothing to store yet
               }
               if constexpr (F32OUT) {
 #pragma unroll
@@ -531,9 +556,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             __syncwarp();
             // ---- phase 2: coalesced global IO; 8 lanes cover one 128-byte row segment, 4 rows per pass, all
             //      eight passes' loads issued before the first store (the residual may alias the output)
-            const int ncol0 = n_blk * BLOCK_N + col_base + c0;  // first GEMM column of this staging chunk
-            const bool col_ok = (sub * ELEMS_PER_CHUNK < NCOLS_HERE) && (ncol0 + sub * ELEMS_PER_CHUNK) < p.N;
-            const long long coff = n_base + col_base + c0 + sub * ELEMS_PER_CHUNK;  // output channel
+            // first output column of this staging chunk (SwiGLU: half the GEMM column)
+            const int ncol0 = SWI ? ((n_blk * BLOCK_N + col_base) >> 1) + c0 : n_blk * BLOCK_N + col_base + c0;
+            const bool col_ok = (sub * ELEMS_PER_CHUNK < NCOLS_HERE) && (ncol0 + sub * ELEMS_PER_CHUNK) < (SWI ? p.N >> 1 : p.N);
+            const long long coff = SWI ? (long long)ncol0 + sub * ELEMS_PER_CHUNK
+                                       : (long long)n_base + col_base + c0 + sub * ELEMS_PER_CHUNK;  // output channel
             if constexpr (F32OUT) {
               const long long(&rpix)[8] = res_pix;
               bool ok[8];

@@ -304,35 +304,6 @@ __global__ void relu_copy_kernel(const T* __restrict__ in, T* __restrict__ out, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// SwiGLU gate (ViT-G, misc_helpers.py:181-184): out[m, j] = silu(in[m, j]) * in[m, h + j], in [M, 2h], out [M, hp] with
-// columns [h, hp) zeroed (hp = h rounded up to the GEMM K chunk). 8 columns per thread.
-template <typename T>
-__global__ void swiglu_kernel(const T* __restrict__ in, T* __restrict__ out, long long M, int h, int hp) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int cv = hp >> 3;
-  const long long total = M * cv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv) * 8;
-    const long long m = idx / cv;
-    Vec8<T> o;
-    if (c8 < h) {  // h is a multiple of 8
-      const Vec8<T> g = *reinterpret_cast<const Vec8<T>*>(in + m * 2 * h + c8);
-      const Vec8<T> l = *reinterpret_cast<const Vec8<T>*>(in + m * 2 * h + h + c8);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float gv = to_f32(g.v[k]);
-        o.v[k] = from_f32<T>(gv / (1.0f + __expf(-gv)) * to_f32(l.v[k]));
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = from_f32<T>(0.0f);
-    }
-    *reinterpret_cast<Vec8<T>*>(out + m * hp + c8) = o;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // fp32 -> 16-bit cast (BEiT taps: the encoder has no output norm), 4 elements per thread
 template <typename T>

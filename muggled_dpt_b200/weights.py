@@ -116,6 +116,23 @@ def fold_layernorm(w: torch.Tensor, b, ln_w: torch.Tensor, ln_b: torch.Tensor):
     return pack_linear(w * ln_w.to(torch.float32)[None, :]), b2
 
 
+def interleave_swiglu(w12: torch.Tensor, b12: torch.Tensor):
+    """Doubled inner Linear of the SwiGLU FFN (components/misc_helpers.py:161-184: rows [0, h) are the gate half, rows
+    [h, 2h) the linear half) -> rows in blocks of 64 = 32 gate rows followed by the 32 linear rows of the same features,
+    h zero-padded to hp = roundup(h, 64): [2 hp, K] and [2 hp]. The GEMM epilogue (csrc/gemm_tc.cuh ACT_SWIGLU) then
+    holds both halves of a feature in one thread and writes silu(gate) * linear directly; the zero rows produce the
+    zero columns [h, hp) that the outer Linear's K padding expects."""
+    h = w12.shape[0] // 2
+    hp = _roundup(h, GEMM_K)
+    j = torch.arange(h)
+    dst_gate = (j // 32) * 64 + (j % 32)
+    w = w12.new_zeros(2 * hp, w12.shape[1])
+    b = b12.new_zeros(2 * hp)
+    w[dst_gate], w[dst_gate + 32] = w12[:h], w12[h:]
+    b[dst_gate], b[dst_gate + 32] = b12[:h], b12[h:]
+    return w, b
+
+
 def pack_conv(w: torch.Tensor) -> torch.Tensor:
     """Conv2d weight [Cout, Cin, kh, kw] -> [Cout, kh*kw*kpad], column = (ky*kw + kx)*kpad + ci"""
     co, ci, kh, kw = w.shape
@@ -241,9 +258,12 @@ def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
             put(d + "proj.b", g1 * b, "f32")
         if cfg.get("is_giant", False):
             # ViT-G: SwiGLU FFN (components/misc_helpers.py:125-185) - w12 is the doubled inner Linear (gate half first),
-            # w3 the outer Linear; they take the places of fc1 / fc2 (dpt_config.mlp_swiglu)
+            # w3 the outer Linear; they take the places of fc1 / fc2 (dpt_config.mlp_swiglu), fc1 with its rows
+            # interleaved for the fused gate epilogue
             w1, b1 = get(s + "mlp.w12.weight"), get(s + "mlp.w12.bias")
             w, b = get(s + "mlp.w3.weight"), get(s + "mlp.w3.bias")
+            if w1 is not None and b1 is not None:
+                w1, b1 = interleave_swiglu(w1, b1)
         else:
             w1, b1 = get(s + "mlp.fc1.weight", (4 * F, F)), get(s + "mlp.fc1.bias", (4 * F,))
             w, b = get(s + "mlp.fc2.weight", (F, 4 * F)), get(s + "mlp.fc2.bias", (F,))

@@ -22,7 +22,8 @@ def conv_gemm(A, Wt, bias=None, add1=None, add2=None, want_relu=False, taps=1, x
     """A [B,H,W,C] 16-bit, Wt [N, taps*kpad] 16-bit -> out [B,H,W-xoff,N]"""
     B, H, W, Cc = A.shape
     n = N_out if N_out is not None else Wt.shape[0]
-    out = torch.empty((B, H, W - xoff, n), device=A.device, dtype=torch.float32 if out_f32 else A.dtype)
+    n_cols = n // 2 if act == 4 else n  # act 4 = SwiGLU gate in the epilogue: half as many output columns
+    out = torch.empty((B, H, W - xoff, n_cols), device=A.device, dtype=torch.float32 if out_f32 else A.dtype)
     out_relu = torch.empty_like(out) if want_relu else None
     rc = N.lib().dpt_op_conv_gemm(_p(A), _p(Wt), _p(bias), _p(out), _p(add1), _p(add2), _p(out_relu), B, H, W, Cc, n,
                                   taps, xoff, act, int(out_f32), DT[A.dtype], _stream())

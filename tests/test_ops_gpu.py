@@ -265,6 +265,28 @@ def test_gemm_two_cta_pairs(M, K, N, act, dtype):
     assert torch.isfinite(out.float()).all()
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,K,h", [(300, 128, 344), (1297, 1536, 4096), (20752, 1536, 4096), (9000, 256, 96)])
+def test_gemm_swiglu_epilogue(M, K, h, dtype):
+    """act 4: the doubled inner Linear of the ViT-G FFN with interleaved rows (weights.interleave_swiglu); the epilogue
+    writes silu(gate) * linear (misc_helpers.py:181-184) - single-CTA 128 / 256 tiles and CTA pairs, padded hidden"""
+    from gpu_util import conv_gemm, rel_err
+    from muggled_dpt_b200.weights import interleave_swiglu
+
+    A = _mk((1, 1, M, K), dtype, 51)
+    W12 = _mk((2 * h, K), dtype, 52, K**-0.5 * 1.5)
+    b12 = _mk((2 * h,), torch.float32, 53, 0.3)
+    Wp, bp = interleave_swiglu(W12, b12)
+    hp = Wp.shape[0] // 2
+    assert hp % 64 == 0 and hp >= h
+    out = conv_gemm(A, pack_linear(Wp), bp, act=4).reshape(M, hp)
+    pre = A.float().reshape(M, K) @ W12.float().t() + b12
+    ref = F.silu(pre[:, :h]) * pre[:, h:]
+    rel, mx = rel_err(out[:, :h], ref)
+    assert rel < _tol(dtype), (rel, mx)
+    assert torch.count_nonzero(out[:, h:]) == 0  # the padding columns are written, as zeros
+
+
 def test_gemm_two_cta_f32_residual_inplace():
     from gpu_util import rel_err
     import ctypes as C

