@@ -1352,38 +1352,32 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
     }
     void* res = proj;
     int rh = gh, rw = gw;
+    int Rp = R;  // channels of `res` (ConvTranspose outputs are padded to 32)
     if (k == 0 || k == 1) {
       // ConvTranspose2d(k = s, stride = s) == s*s GEMMs with pixel-shuffled stores
       const int s = k == 0 ? 4 : 2;
       const Weight *uw = get_w(c, pre + "up.w", hd), *ub = get_w(c, pre + "up.b", DPT_F32);
       if (!c.ok) return false;
       rh = gh * s; rw = gw * s;
-      res = c.ar.alloc((size_t)B * rh * rw * R * 2);
-      const long long rows_per_sub = uw->shape[0] / (s * s);
+      // the packer pads the output channels to whole 32-column tiles (zero rows / zero bias), so a tile always lies
+      // inside one sub-pixel block and all s*s blocks run as ONE launch with pixel-shuffled stores; `res` carries the
+      // padded channels (zeros), which the fuse convolution's zero K-padding ignores
       const int kpad = (int)uw->shape[1];
-      // one launch when the channel count is a whole number of n-tiles (the tile then lies inside one sub-pixel block):
-      // the cost model's choice for multiples of 256 / 128 channels, else the widest tile that divides R (ViT-B: 96 -> 32,
-      // 192 -> 64; ViT-S: 48 -> s*s launches)
-      int bn_forced = 0;  // multiples of 256: any tile width the cost model picks divides R
-      if (R % 256 != 0) bn_forced = R % 128 == 0 ? 128 : (R % 64 == 0 ? 64 : (R % 32 == 0 ? 32 : -1));
-      if (bn_forced >= 0) {
-        GemmOp op;
-        op.A = proj; op.B = B; op.Ht = gh; op.Wt = gw; op.C = R;
-        op.Wt_ptr = uw->ptr; op.N = s * s * R; op.kpad = kpad; op.ldo = R;
-        op.bias = (const float*)ub->ptr; op.out = res;
-        op.so = s; op.shuffle_n = R; op.OH = rh; op.OW = rw; op.label = "convT";
-        op.force_bn = bn_forced;
-        add_gemm(c, op);
-      } else
-      for (int sub = 0; sub < s * s; ++sub) {
-        GemmOp op;
-        op.A = proj; op.B = B; op.Ht = gh; op.Wt = gw; op.C = R;
-        op.Wt_ptr = (const char*)uw->ptr + (size_t)sub * rows_per_sub * kpad * 2;
-        op.N = R; op.kpad = kpad;
-        op.bias = (const float*)ub->ptr; op.out = res;
-        op.so = s; op.oy = sub / s; op.ox = sub % s; op.OH = rh; op.OW = rw; op.label = "convT";
-        add_gemm(c, op);
-      }
+      Rp = (int)(uw->shape[0] / (s * s));
+      if (Rp < R || Rp % 32 != 0 || uw->shape[0] != (long long)s * s * Rp || ub->shape[0] != Rp)
+        return c.fail("reassembly: ConvTranspose weights must be packed with the output channels padded to 32");
+      res = c.ar.alloc((size_t)B * rh * rw * Rp * 2);
+      // tile width: the cost model's choice for multiples of 256 channels, else the widest tile that divides the
+      // (padded) channel count (ViT-B: 96 -> 32, 192 -> 64; ViT-S: 48 -> 64, 96 -> 32)
+      int bn_forced = 0;
+      if (Rp % 256 != 0) bn_forced = Rp % 128 == 0 ? 128 : (Rp % 64 == 0 ? 64 : 32);
+      GemmOp op;
+      op.A = proj; op.B = B; op.Ht = gh; op.Wt = gw; op.C = R;
+      op.Wt_ptr = uw->ptr; op.N = s * s * Rp; op.kpad = kpad; op.ldo = Rp;
+      op.bias = (const float*)ub->ptr; op.out = res;
+      op.so = s; op.shuffle_n = Rp; op.OH = rh; op.OW = rw; op.label = "convT";
+      op.force_bn = bn_forced;
+      add_gemm(c, op);
     } else if (k == 3) {
       // Conv2d(k=3, s=2, p=1): im2col gather + GEMM
       const Weight *dw = get_w(c, pre + "down.w", hd), *db = get_w(c, pre + "down.b", DPT_F32);
@@ -1411,8 +1405,9 @@ bool build_reassemble(Ctx& c, const void* const taps[4], void* const maps[4], vo
     {
       // fuse_proj: 3x3, R -> C, no bias
       GemmOp op;
-      op.A = res; op.B = B; op.Ht = rh; op.Wt = rw; op.C = R;
+      op.A = res; op.B = B; op.Ht = rh; op.Wt = rw; op.C = Rp;
       op.Wt_ptr = fw->ptr; op.N = C; op.taps = 9; op.kpad = (int)fw->shape[1] / 9;
+      if (op.kpad < Rp) return c.fail("reassembly: fuse convolution K padding is narrower than its input");
       op.out = maps[k];
       op.out2_relu = maps_relu ? maps_relu[k] : nullptr;
       op.label = "fuse3x3";

@@ -142,16 +142,31 @@ def pack_conv(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(co, kh * kw * kpad)
 
 
+CONVT_CH = 32  # ConvTranspose output channels are padded to whole 32-column GEMM tiles
+
+
 def pack_conv_transpose(w: torch.Tensor) -> torch.Tensor:
-    """ConvTranspose2d(k = stride = s) weight [Cin, Cout, s, s] -> [s*s*Cout, kpad]; block (ky*s + kx) holds
-    W_sub[co, ci] = w[ci, co, ky, kx], so out[b, y*s+ky, x*s+kx, co] = sum_ci in[b,y,x,ci] * W_sub[co, ci] + bias[co]
-    (reassembly_model.py:262-269)."""
+    """ConvTranspose2d(k = stride = s) weight [Cin, Cout, s, s] -> [s*s*cop, kpad], cop = roundup(Cout, 32); block
+    (ky*s + kx) holds W_sub[co, ci] = w[ci, co, ky, kx], so out[b, y*s+ky, x*s+kx, co] = sum_ci in[b,y,x,ci] *
+    W_sub[co, ci] + bias[co] (reassembly_model.py:262-269). The zero rows [Cout, cop) make every sub-pixel block a whole
+    number of GEMM n-tiles, so all s*s blocks run as ONE launch with pixel-shuffled stores for any channel count (ViT-S:
+    48 -> 64); the padded output channels are zeros that the next convolution's zero K-padding ignores."""
     ci, co, s, s2 = w.shape
     assert s == s2
     kpad = _roundup(ci, GEMM_K)
-    out = w.new_zeros(s * s, co, kpad)
-    out[:, :, :ci] = w.permute(2, 3, 1, 0).reshape(s * s, co, ci)
-    return out.reshape(s * s * co, kpad)
+    cop = _roundup(co, CONVT_CH)
+    out = w.new_zeros(s * s, cop, kpad)
+    out[:, :co, :ci] = w.permute(2, 3, 1, 0).reshape(s * s, co, ci)
+    return out.reshape(s * s * cop, kpad)
+
+
+def pad_conv_transpose_bias(b):
+    """bias [Cout] -> [roundup(Cout, 32)] (zeros), matching pack_conv_transpose"""
+    if b is None:
+        return None
+    out = b.new_zeros(_roundup(b.shape[0], CONVT_CH))
+    out[: b.shape[0]] = b
+    return out
 
 
 def pack_patch_embed(w: torch.Tensor) -> torch.Tensor:
@@ -285,7 +300,7 @@ def pack_depthanything_v2(sd: dict, cfg: dict, strict: bool = True) -> dict:
         if k in (0, 1):
             w = get(f"depth_head.resize_layers.{k}.weight")
             put(d + "up.w", pack_conv_transpose(w) if w is not None else None, "half")
-            put(d + "up.b", get(f"depth_head.resize_layers.{k}.bias"), "f32")
+            put(d + "up.b", pad_conv_transpose_bias(get(f"depth_head.resize_layers.{k}.bias")), "f32")
         elif k == 3:
             w = get("depth_head.resize_layers.3.weight")
             put(d + "down.w", pack_conv(w) if w is not None else None, "half")
@@ -425,7 +440,7 @@ def pack_beit(sd: dict, cfg: dict, strict: bool = True) -> dict:
         if k in (0, 1):
             w = get(s + "4.weight")
             put(d + "up.w", pack_conv_transpose(w) if w is not None else None, "half")
-            put(d + "up.b", get(s + "4.bias"), "f32")
+            put(d + "up.b", pad_conv_transpose_bias(get(s + "4.bias")), "f32")
         elif k == 3:
             put(d + "down.w", conv(s + "4.weight"), "half")
             put(d + "down.b", get(s + "4.bias"), "f32")

@@ -37,12 +37,17 @@ def test_pack_conv_transpose_matches_conv_transpose2d(s):
     w = torch.randn(ci, co, s, s)
     b = torch.randn(co)
     packed = Wt.pack_conv_transpose(w)
-    assert packed.shape == (s * s * co, 64)
+    cop = 32  # output channels padded to whole 32-column tiles (zero rows), the bias with them
+    assert packed.shape == (s * s * cop, 64)
+    bp = Wt.pad_conv_transpose_bias(b)
+    assert bp.shape == (cop,) and torch.count_nonzero(bp[co:]) == 0
     xp = F.pad(x, (0, 64 - ci))
     out = torch.zeros(2, 5 * s, 6 * s, co)
     for sub in range(s * s):
         ky, kx = sub // s, sub % s
-        out[:, ky::s, kx::s, :] = xp @ packed[sub * co:(sub + 1) * co].t() + b
+        full = xp @ packed[sub * cop:(sub + 1) * cop].t() + bp
+        assert torch.count_nonzero(full[..., co:]) == 0
+        out[:, ky::s, kx::s, :] = full[..., :co]
     ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), w, b, stride=s).permute(0, 2, 3, 1)
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
 
