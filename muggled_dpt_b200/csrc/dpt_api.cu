@@ -297,6 +297,10 @@ cudaError_t launch_gemm2_inst(const GemmParams& p, int grid, cudaStream_t s) {
 
 template <bool BF16>
 cudaError_t launch_gemm2_dt(const GemmParams& p, int bn, int grid, cudaStream_t s) {
+  if (bn == 384) {  // 256 x 384 pair tiles: fp32 residual outputs whose m-pairs x 3 n-tiles fit ONE round (small M)
+    return use_respf(p) ? launch_gemm2_inst<OUT_F32, ACT_NONE, BF16, true, 384>(p, grid, s)
+                        : launch_gemm2_inst<OUT_F32, ACT_NONE, BF16, false, 384>(p, grid, s);
+  }
   if (bn == 128) {  // 256 x 128 pair tiles: 16-bit outputs without GELU (3x3 convolutions), fp32 residual outputs (small M)
     if (p.out_kind == OUT_F32)
       return use_respf(p) ? launch_gemm2_inst<OUT_F32, ACT_NONE, BF16, true, 128>(p, grid, s)
@@ -353,6 +357,25 @@ double cost_pair128() {
   return v;
 }
 
+// 256 x 384 pair tiles: cost of the single round they run in, in units of a 256 x 256 pair tile (1.5 by area);
+// DPT_COST_PAIR384 overrides, DPT_GEMM_WIDE=0 disables them
+double cost_pair384() {
+  static double v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_COST_PAIR384");
+    v = e ? atof(e) : 1.50;
+  }
+  return v;
+}
+bool wide_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_GEMM_WIDE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool two_cta_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -391,6 +414,11 @@ TileChoice choose_tile(long long m_tiles, int N, int num_sms, bool f32_out) {
   const double c_256 = rounds(m_tiles * nt256, num_sms) * kCost256;
   const double c_128 = rounds(m_tiles * nt128, num_sms) * kCost128;
   const double c_pair128 = (pairs_ok && f32_out) ? rounds(pairs * nt128, num_sms / 2) * cost_pair128() : 1e30;
+  // 256 x 384 pair tiles (fp32 outputs): one accumulator stage, so only when everything fits a single round
+  const int nt384 = (N + 383) / 384;
+  const double c_pair384 = (two_cta_enabled() && f32_out && wide_enabled() && pairs * nt384 <= num_sms / 2 &&
+                            pairs * nt384 >= num_sms / 4) ? cost_pair384() : 1e30;
+  if (c_pair384 < c_pair && c_pair384 < c_256 && c_pair384 < c_128 && c_pair384 < c_pair128) return {384, true};
   if (c_pair128 < c_pair && c_pair128 < c_256 && c_pair128 < c_128) return {128, true};
   if (c_pair <= c_256 && c_pair <= c_128) return {256, true};
   return c_256 <= c_128 ? TileChoice{256, false} : TileChoice{128, false};
@@ -493,7 +521,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
     const uint64_t ktot = (uint64_t)op.taps * op.kpad;
     uint64_t dims[2] = {ktot, (uint64_t)op.N};
     uint64_t str[1] = {ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)(two_cta ? bn / 2 : bn)};
+    uint32_t box[2] = {64, (uint32_t)(bn == 384 ? 64 : (two_cta ? bn / 2 : bn))};  // 384: three 64-row boxes per CTA
     if (!make_tmap(&p.tmB, op.Wt_ptr, 2, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
   }
   p.W = op.W; p.H = op.H; p.B = op.B;
@@ -521,6 +549,8 @@ bool add_gemm(Ctx& c, GemmOp op) {
   p.add1 = op.add1; p.ld_add1 = op.ld_add1 ? op.ld_add1 : op.ldo;
   p.add2 = op.add2; p.ld_add2 = op.ld_add2 ? op.ld_add2 : op.ldo;
   p.out2_relu = op.out2_relu; p.ld_out2 = op.ld_out2 ? op.ld_out2 : op.ldo;
+  if (bn == 384 && (op.ln_stats != nullptr || op.out_kind != OUT_F32 || !two_cta))
+    return c.fail("gemm: 384-wide tiles are CTA-pair fp32-output tiles without a folded LayerNorm");
   if (op.ln_stats != nullptr) {
     if (op.ln_colsum == nullptr || op.ln_parts <= 0 || (op.ln_parts & 1) || op.N < 32) return c.fail("gemm: folded LayerNorm needs colsum / parts");
     p.ln_stats = op.ln_stats; p.ln_parts = op.ln_parts; p.ln_colsum = op.ln_colsum;

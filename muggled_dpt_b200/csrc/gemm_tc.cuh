@@ -96,17 +96,24 @@ struct __align__(64) GemmParams {
 // residual of the next 32-column unit - and pay for it with one pipeline stage.
 template <int BLOCK_N, bool TWO_CTA = false, bool F32OUT = false>
 struct GemmCfg {
-  static constexpr int STAGES_BASE = TWO_CTA ? (BLOCK_N == 256 ? 6 : 8) : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
-  static constexpr int STAGES = !F32OUT ? STAGES_BASE
+  // BLOCK_N = 384 (CTA pairs, fp32 outputs only): 256 x 384 tiles for the small-M residual GEMMs - three n-tiles cover
+  // N = 1024, so up to 24 m-pairs (M <= 6144) finish in ONE round on 72 of the 74 SM pairs where 128 x 128 tiles need
+  // three. One accumulator stage (384 of the 512 TMEM columns), two MMAs per K step (N = 256 + N = 128), 4 stages.
+  static constexpr bool WIDE = BLOCK_N == 384;
+  static constexpr int ACC_STAGES = WIDE ? 1 : 2;
+  static constexpr int STAGES_BASE = WIDE ? 4 : (TWO_CTA ? (BLOCK_N == 256 ? 6 : 8) : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8)));
+  static constexpr int STAGES = (!F32OUT || WIDE) ? STAGES_BASE
                                 : (BLOCK_N == 64 ? 6 : (BLOCK_N == 32 ? 8 : ((TWO_CTA && BLOCK_N == 128) ? STAGES_BASE - 2 : STAGES_BASE - 1)));
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = (TWO_CTA ? BLOCK_N / 2 : BLOCK_N) * GEMM_BLOCK_K * 2;
   static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP;
   static constexpr int RES_BYTES = F32OUT ? GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP : 0;
-  static constexpr int BAR_BYTES = 256 + 2 * BLOCK_N * 4;  // mbarriers + tmem ptr, bias tile + colsum tile [BLOCK_N] each
+  // mbarriers + tmem ptr, bias tile + colsum tile [BLOCK_N] each (the wide fp32-output tiles have no folded LayerNorm)
+  static constexpr int VEC_TILES = WIDE ? 1 : 2;
+  static constexpr int BAR_BYTES = 256 + VEC_TILES * BLOCK_N * 4;
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + RES_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-  static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+  static constexpr int TMEM_COLS = WIDE ? 512 : ((2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N));
 };
 
 DPT_DEVICE float gelu_erf(float x) {
@@ -167,7 +174,10 @@ template <int BLOCK_N, int OUT_KIND, int ACT, bool BF16, bool TWO_CTA = false, b
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   static_assert(!RESPF || OUT_KIND == OUT_F32, "residual prefetch exists for fp32 outputs only");
   using Cfg = GemmCfg<BLOCK_N, TWO_CTA, RESPF>;
-  static_assert(!TWO_CTA || BLOCK_N == 256 || BLOCK_N == 128, "the 2-CTA kernel is built for BLOCK_N = 256 and 128");
+  static_assert(!TWO_CTA || BLOCK_N == 384 || BLOCK_N == 256 || BLOCK_N == 128, "the 2-CTA kernel is built for BLOCK_N = 384, 256 and 128");
+  static_assert(BLOCK_N != 384 || (TWO_CTA && OUT_KIND == OUT_F32), "384-wide tiles: CTA pairs with fp32 output only");
+  constexpr bool WIDE = Cfg::WIDE;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
   constexpr int STAGES = Cfg::STAGES;
 
   // no static shared memory in this kernel: the dynamic segment starts at the CTA's (1024-aligned) window base;
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint8_t* staging = smem_b + STAGES * Cfg::B_BYTES;
   uint8_t* resbuf = staging + Cfg::STAGING_BYTES;  // OUT_F32: per-warp prefetched residual unit
   float* bias_s = reinterpret_cast<float*>(resbuf + Cfg::RES_BYTES);  // bias [BLOCK_N] | LN colsum [BLOCK_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BLOCK_N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + Cfg::VEC_TILES * BLOCK_N);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -254,6 +264,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               // the leader's barrier collects the bytes of both CTAs; completion is signalled there
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
               tma_load_4d_2sm(smem_a + s * Cfg::A_BYTES, &p.tmA, &full_bar[s], kc * GEMM_BLOCK_K, x0 + dx, y0 + dy, b);
+              if constexpr (WIDE) {
+                // my half of the N = 256 MMA's B rows (two 64-row boxes), then my half of the N = 128 MMA's
+                const int kx = (tap * p.kchunks + kc) * GEMM_BLOCK_K;
+                uint8_t* sb = smem_b + s * Cfg::B_BYTES;
+                tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], kx, n_blk * BLOCK_N + (int)cta_rank * 128);
+                tma_load_2d_2sm(sb + 8192, &p.tmB, &full_bar[s], kx, n_blk * BLOCK_N + (int)cta_rank * 128 + 64);
+                tma_load_2d_2sm(sb + 16384, &p.tmB, &full_bar[s], kx, n_blk * BLOCK_N + 256 + (int)cta_rank * 64);
+              } else
               tma_load_2d_2sm(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], (tap * p.kchunks + kc) * GEMM_BLOCK_K,
                               n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
             } else {
@@ -271,13 +289,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer =====================================
     if (cta_rank == 0 && elect_one()) {  // 2-CTA: only the leader issues MMAs (for both CTAs)
-      const uint32_t idesc = make_idesc_f16(TWO_CTA ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, BLOCK_N, BF16, false, false);
+      const uint32_t idesc = make_idesc_f16(TWO_CTA ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, WIDE ? 256 : BLOCK_N, BF16, false, false);
+      const uint32_t idesc_hi = make_idesc_f16(2 * GEMM_BLOCK_M, 128, BF16, false, false);  // WIDE: columns [256, 384)
+      (void)idesc_hi;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       for (int tile = work_first; tile < total_tiles; tile += work_stride, ++it) {
-        const int as = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
+        const int as = ACC_STAGES == 2 ? (it & 1) : 0;
+        const uint32_t aph = ACC_STAGES == 2 ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -286,11 +306,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES));
           const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES));
+          const uint64_t b_desc_hi = WIDE ? make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES + 16384)) : 0;
+          (void)b_desc_hi;
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
             if constexpr (TWO_CTA) umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (WIDE)  // B rows 128.. of each CTA's stage
+              umma_f16_ss_2sm(d_tmem + 256, a_desc + 2 * k, b_desc_hi + 2 * k, idesc_hi, (kb | k) != 0 ? 1u : 0u);
           }
           if constexpr (TWO_CTA) umma_commit_2sm(&empty_bar[s]);  // frees the stage in both CTAs
           else umma_commit(&empty_bar[s]);
@@ -316,8 +340,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0;
     for (int tile = work_first; tile < total_tiles; tile += work_stride, ++it) {
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
+      const int as = ACC_STAGES == 2 ? (it & 1) : 0;
+      const uint32_t aph = ACC_STAGES == 2 ? ((it >> 1) & 1) : (it & 1);
       const int n_blk = tile % p.n_tiles;
       int mt = (tile / p.n_tiles) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
       const int tx = mt % p.tiles_x;
@@ -348,11 +372,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       float* bs = bias_s;
       float* cs = bias_s + BLOCK_N;
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
-      if (et < BLOCK_N) {
-        const int n = n_blk * BLOCK_N + et;
+#pragma unroll
+      for (int e = et; e < BLOCK_N; e += GEMM_EPI_WARPS * 32) {
+        const int n = n_blk * BLOCK_N + e;
         const bool in = n < p.N && b < p.B;
-        bs[et] = (p.bias != nullptr && in) ? __ldg(p.bias + (long long)b * p.bias_bstride + (n_base + et)) : 0.0f;
-        cs[et] = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n) : 0.0f;
+        bs[e] = (p.bias != nullptr && in) ? __ldg(p.bias + (long long)b * p.bias_bstride + (n_base + e)) : 0.0f;
+        if constexpr (!WIDE) cs[e] = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n) : 0.0f;
       }
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
 
@@ -464,7 +489,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             {
               const float4* b4 = reinterpret_cast<const float4*>(bs + gc);
               float f[32];
-              if (p.ln_stats != nullptr) {
+              if (!WIDE && p.ln_stats != nullptr) {
                 const float4* s4 = reinterpret_cast<const float4*>(cs + gc);
                 const float2 rs2 = make_float2(ln_rstd, ln_rstd), rm2 = make_float2(ln_rm, ln_rm);
 #pragma unroll

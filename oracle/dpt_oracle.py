@@ -246,6 +246,8 @@ STANDARD_CONFIGS = {
     "vitl": dict(F=1024, blocks=24, reasm=(256, 512, 1024, 1024), C=256),
     # vit-giant dimensions (make_depthanythingv2_dpt.py:88-95); pass the result through giantify() for its SwiGLU FFN
     "vitg": dict(F=1536, blocks=40, reasm=(1536, 1536, 1536, 1536), C=384),
+    # ViT-L widths with 4 blocks: the small-batch tile choices of the 1024-wide GEMMs at oracle-friendly cost
+    "vitl_4blk": dict(F=1024, blocks=4, reasm=(256, 512, 1024, 1024), C=256),
     # not a real model: small enough to commit its weights-free fixtures and run anywhere in milliseconds
     "tiny": dict(F=128, blocks=4, reasm=(16, 32, 64, 128), C=32),
     # 8 blocks: the V1 tap rule (last four blocks) and the V2 rule (every second block) differ

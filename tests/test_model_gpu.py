@@ -135,6 +135,36 @@ def test_vits_504_against_oracle():
         gate(f"dav2.vits504.{_dt(dtype)}.depth.max_rel", e[2], DEPTH_MAXREL[dtype])
 
 
+def test_small_batch_wide_pair_tiles_against_oracle():
+    """B = 4 at 504^2 with ViT-L widths (M = 5188 rows, the per-GPU shard of the 8-GPU strong-scaling run): the fp32
+    residual GEMMs (proj, fc2: N = 1024) run as 256 x 384 CTA-pair tiles in one round (gemm_tc.cuh BLOCK_N = 384, with
+    and without the residual prefetch), writing the row statistics and the 16-bit copy the next GEMM reads."""
+    from oracle import dpt_oracle as O
+
+    sd = O.make_synthetic_state_dict("vitl_4blk", seed=17)
+    img = O.make_input(4, 504, 504, seed=5)
+    ref = O.forward(sd, img, return_stages=True)
+    for dtype in (torch.bfloat16, torch.float16):
+        cfg, model = _load_model(sd, dtype)
+        with torch.inference_mode():
+            x = img.to("cuda", dtype)
+            tokens, grid = model.patch_embed(x)
+            taps = model.imgencoder(tokens, grid)
+            model.enable_profiling(True)
+            depth = model(x)
+            torch.cuda.synchronize()
+            labels = [r[0] for r in model.read_profile()]
+            model.enable_profiling(False)
+        assert sum(l.startswith("gemm384x2:") and l.endswith(".proj") for l in labels) == 4, labels[:12]
+        assert sum(l.startswith("gemm384x2:") and l.endswith(".fc2") for l in labels) == 4
+        for i in range(4):
+            e = _err(taps[i], ref["taps"][i])
+            gate(f"dav2.vitl_4blk_B4.{_dt(dtype)}.tap{i}.rel_l2", e[0], REL_L2[dtype])
+        e = _err(depth, ref["depth"])
+        gate(f"dav2.vitl_4blk_B4.{_dt(dtype)}.depth.rel_l2", e[0], 2 * REL_L2[dtype])
+        gate(f"dav2.vitl_4blk_B4.{_dt(dtype)}.depth.max_rel", e[2], DEPTH_MAXREL[dtype])
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_wide_reassembly_merged_conv_transpose_against_oracle(dtype):
     """256 reassembly channels (the ViT-L case): ConvTranspose2d k=s=4 / k=s=2 run as ONE pixel-shuffling GEMM launch

@@ -308,6 +308,29 @@ def test_gemm_two_cta_f32_residual_inplace():
     assert rel < 1e-3, (rel, mx)
 
 
+@pytest.mark.parametrize("M,K,N", [(5188, 1024, 1024), (5188, 4096, 1024), (6144, 512, 1000), (4800, 1536, 904)])
+def test_gemm_wide_pair_tiles_f32_residual_inplace(M, K, N):
+    """shapes the cost model gives to the 256 x 384 CTA-pair tiles (38..48 m-tiles, 897..1024 columns): short K (residual
+    prefetch variant) and long K, a ragged last n-tile, an odd trailing m-tile"""
+    from gpu_util import rel_err
+    import ctypes as C
+    from muggled_dpt_b200 import _native as NN
+
+    A = _mk((1, 1, M, K), torch.bfloat16, 61)
+    W = _mk((N, K), torch.bfloat16, 62, K**-0.5)
+    bias = _mk((N,), torch.float32, 63)
+    x = _mk((M, N), torch.float32, 64)
+    ref = x + A.float().reshape(M, K) @ W.float().t() + bias
+    Wp = pack_linear(W)
+    rc = NN.lib().dpt_op_conv_gemm(A.data_ptr(), Wp.data_ptr(), bias.data_ptr(), x.data_ptr(), x.data_ptr(), None, None,
+                                   1, 1, M, K, N, 1, 0, 0, 1, NN.DPT_BF16,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    NN.check(rc, None, "gemm")
+    torch.cuda.synchronize()
+    rel, mx = rel_err(x, ref)
+    assert rel < 1e-3, (rel, mx)
+
+
 def test_conv3x3_two_cta_pairs_128_wide():
     """N = 128 convolution large enough (>= 296 tile pairs) for the 256 x 128 CTA-pair kernel (head c1 at full size)"""
     from gpu_util import conv_gemm, rel_err
