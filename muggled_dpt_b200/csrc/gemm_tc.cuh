@@ -136,23 +136,24 @@ DPT_DEVICE float gelu_erf(float x) {
 }
 
 // two GELUs at once with packed fp32x2 FMA (sm_100 FFMA2): same formula as gelu_erf
+// two GELUs at once with packed fp32x2 FMA (sm_100 FFMA2). Same erf approximation as gelu_erf, arranged for fewer
+// instructions: with a = |x| and r = 1 - erf(a / sqrt 2) = p(a)^-16 (the sqrt 2 folded into the coefficients),
+// gelu(x) = relu(x) - 0.5 a r   [x >= 0: 0.5 x (2 - r); x < 0: 0.5 x r] - no copysign, no 1 - r.
 DPT_DEVICE float2 gelu_erf2(float2 x) {
-  const float2 z = make_float2(fabsf(x.x) * 0.70710678118654752f, fabsf(x.y) * 0.70710678118654752f);
-  float2 p = __ffma2_rn(z, make_float2(0.0000430638f, 0.0000430638f), make_float2(0.0002765672f, 0.0002765672f));
-  p = __ffma2_rn(z, p, make_float2(0.0001520143f, 0.0001520143f));
-  p = __ffma2_rn(z, p, make_float2(0.0092705272f, 0.0092705272f));
-  p = __ffma2_rn(z, p, make_float2(0.0422820123f, 0.0422820123f));
-  p = __ffma2_rn(z, p, make_float2(0.0705230784f, 0.0705230784f));
-  p = __ffma2_rn(z, p, make_float2(1.0f, 1.0f));
+  const float2 a = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 p = __ffma2_rn(a, make_float2(5.3829750e-06f, 5.3829750e-06f), make_float2(4.8890636e-05f, 4.8890636e-05f));
+  p = __ffma2_rn(a, p, make_float2(3.8003575e-05f, 3.8003575e-05f));
+  p = __ffma2_rn(a, p, make_float2(3.2776263e-03f, 3.2776263e-03f));
+  p = __ffma2_rn(a, p, make_float2(2.1141006e-02f, 2.1141006e-02f));
+  p = __ffma2_rn(a, p, make_float2(4.9867347e-02f, 4.9867347e-02f));
+  p = __ffma2_rn(a, p, make_float2(1.0f, 1.0f));
   p = __fmul2_rn(p, p);
   p = __fmul2_rn(p, p);
   p = __fmul2_rn(p, p);
   p = __fmul2_rn(p, p);
-  float2 e;
-  e.x = copysignf(1.0f - rcp_approx(p.x), x.x);
-  e.y = copysignf(1.0f - rcp_approx(p.y), x.y);
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(e, hx, hx);
+  const float2 rr = make_float2(rcp_approx(p.x), rcp_approx(p.y));
+  const float2 nh = __fmul2_rn(a, make_float2(-0.5f, -0.5f));
+  return __ffma2_rn(nh, rr, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
 DPT_DEVICE uint32_t pack2(float a, float b, int is_bf16) {
@@ -338,57 +339,85 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     constexpr int is_bf16 = BF16 ? 1 : 0;
     const int r = q * 32 + lane;  // accumulator row (TMEM lane) owned by this thread
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    int it = 0;
-    for (int tile = work_first; tile < total_tiles; tile += work_stride, ++it) {
-      const int as = ACC_STAGES == 2 ? (it & 1) : 0;
-      const uint32_t aph = ACC_STAGES == 2 ? ((it >> 1) & 1) : (it & 1);
-      const int n_blk = tile % p.n_tiles;
+    // Per-tile operands of the epilogue - output pixel of my row, bias / folded-LayerNorm column sums of the n-tile (one
+    // or two columns per thread), the partial row statistics of my row - are fetched ONE TILE AHEAD: their global-load
+    // latency (two dependent L2 round trips per tile otherwise) overlaps the previous tile's units.
+    constexpr int NV = (BLOCK_N + GEMM_EPI_WARPS * 32 - 1) / (GEMM_EPI_WARPS * 32);
+    struct EpiTile {
+      int n_blk, b, n_base;
+      long long pix;
+      bool row_ok;
+      float bias_v[NV], cs_v[NV];
+      float4 st4[4];
+    };
+    auto fetch_tile = [&](int tile, EpiTile& t) {
+      t.n_blk = tile % p.n_tiles;
       int mt = (tile / p.n_tiles) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
-      const int b = mt / p.tiles_y;
+      t.b = mt / p.tiles_y;
       // output pixel of my row
       const int x = tx * TW + (r & (TW - 1));
       const int y = ty * TH + (r >> p.tw_log2);
-      const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
+      t.row_ok = (x < p.W) && (y < p.H) && (t.b < p.B);
       // pixel-shuffle target: fixed per launch, or chosen by the n-tile (merged ConvTranspose)
-      const int sub_px = p.shuffle_n > 0 ? (n_blk * BLOCK_N) / p.shuffle_n : 0;
+      const int sub_px = p.shuffle_n > 0 ? (t.n_blk * BLOCK_N) / p.shuffle_n : 0;
       const int sh_oy = p.shuffle_n > 0 ? sub_px / p.so : p.oy, sh_ox = p.shuffle_n > 0 ? sub_px % p.so : p.ox;
-      const int n_base = p.shuffle_n > 0 ? n_blk * BLOCK_N - sub_px * p.shuffle_n : n_blk * BLOCK_N;  // channel of column 0
-      const long long pix = ((long long)b * p.OH + (long long)y * p.so + sh_oy) * p.OW + (long long)x * p.so + sh_ox;
-
-      // folded LayerNorm: the partial statistics of my row; the loads are issued before the bias barriers below so
-      // that their latency overlaps (ln_parts is even: two (sum, sum sq) pairs per 16-byte load)
-      const bool has_ln = p.ln_stats != nullptr && row_ok;
-      const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + pix * (2 * p.ln_parts));
+      t.n_base = p.shuffle_n > 0 ? t.n_blk * BLOCK_N - sub_px * p.shuffle_n : t.n_blk * BLOCK_N;  // channel of column 0
+      t.pix = ((long long)t.b * p.OH + (long long)y * p.so + sh_oy) * p.OW + (long long)x * p.so + sh_ox;
+      // folded LayerNorm: the partial statistics of my row (ln_parts is even: two (sum, sum sq) pairs per 16-byte load)
+      const bool has_ln = p.ln_stats != nullptr && t.row_ok;
+      const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + t.pix * (2 * p.ln_parts));
       const int n4 = p.ln_parts >> 1;
-      float4 st4[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) st4[k] = (has_ln && k < n4) ? __ldg(sp + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 4; ++k) t.st4[k] = (has_ln && k < n4) ? __ldg(sp + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // bias (and column sums) of the n-tile, zero beyond N / when absent
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int e = et + v * GEMM_EPI_WARPS * 32;
+        const int n = t.n_blk * BLOCK_N + e;
+        const bool in = e < BLOCK_N && n < p.N && t.b < p.B;
+        t.bias_v[v] = (p.bias != nullptr && in) ? __ldg(p.bias + (long long)t.b * p.bias_bstride + (t.n_base + e)) : 0.0f;
+        t.cs_v[v] = (!WIDE && p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n) : 0.0f;
+      }
+    };
+    EpiTile cur;
+    if (work_first < total_tiles) fetch_tile(work_first, cur);
+    int it = 0;
+    for (int tile = work_first; tile < total_tiles; tile += work_stride, ++it) {
+      const int as = ACC_STAGES == 2 ? (it & 1) : 0;
+      const uint32_t aph = ACC_STAGES == 2 ? ((it >> 1) & 1) : (it & 1);
+      const int n_blk = cur.n_blk, b = cur.b, n_base = cur.n_base;
+      const long long pix = cur.pix;
+      const bool row_ok = cur.row_ok;
+      (void)b;
 
-      // bias (and folded-LayerNorm column sums) of this n-tile -> smem, zero beyond N / when absent. Single-buffered:
-      // the first barrier waits until every epilogue warp is done with the previous tile's vectors.
+      // bias / column-sum vectors -> smem. Single-buffered: the first barrier waits until every epilogue warp is done
+      // with the previous tile's vectors.
       float* bs = bias_s;
       float* cs = bias_s + BLOCK_N;
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
 #pragma unroll
-      for (int e = et; e < BLOCK_N; e += GEMM_EPI_WARPS * 32) {
-        const int n = n_blk * BLOCK_N + e;
-        const bool in = n < p.N && b < p.B;
-        bs[e] = (p.bias != nullptr && in) ? __ldg(p.bias + (long long)b * p.bias_bstride + (n_base + e)) : 0.0f;
-        if constexpr (!WIDE) cs[e] = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n) : 0.0f;
+      for (int v = 0; v < NV; ++v) {
+        const int e = et + v * GEMM_EPI_WARPS * 32;
+        if (e < BLOCK_N) {
+          bs[e] = cur.bias_v[v];
+          if constexpr (!WIDE) cs[e] = cur.cs_v[v];
+        }
       }
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
 
       float ln_rstd = 1.0f, ln_rm = 0.0f;
-      if (has_ln) {  // partials summed in a fixed order
+      if (p.ln_stats != nullptr && row_ok) {  // partials summed in a fixed order
         float sum = 0.0f, sq = 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          sum += st4[k].x + st4[k].z;
-          sq += st4[k].y + st4[k].w;
+          sum += cur.st4[k].x + cur.st4[k].z;
+          sq += cur.st4[k].y + cur.st4[k].w;
         }
+        const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + pix * (2 * p.ln_parts));
+        const int n4 = p.ln_parts >> 1;
         for (int i = 4; i < n4; ++i) {
           const float4 t = __ldg(sp + i);
           sum += t.x + t.z;
@@ -398,6 +427,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_f - mean * mean, 0.0f) + p.ln_eps);
         ln_rm = -ln_rstd * mean;
       }
+      // the next tile's operands: in flight while this tile's units are processed
+      if (tile + work_stride < total_tiles) fetch_tile(tile + work_stride, cur);
 
       // OUT_F32: rows 4*i + (lane >> 3) of this warp are the ones this lane moves in the coalesced phase. The fp32
       // residual of a 32-column unit is fetched one unit ahead with cp.async into a per-warp buffer (unit 0: before the
