@@ -376,6 +376,16 @@ bool wide_enabled() {
   return v == 1;
 }
 
+// DPT_TMA_STORE=0: every 16-bit output goes through the shuffle + st.global path (A/B switch)
+bool tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DPT_TMA_STORE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool two_cta_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -530,6 +540,19 @@ bool add_gemm(Ctx& c, GemmOp op) {
   p.tiles_y = (op.H + TH - 1) / TH;
   p.N = op.N;
   p.n_tiles = (op.N + bn - 1) / bn;
+  // plain 16-bit outputs leave through the TMA (gemm_tc.cuh tma_store): box = the 32 rows of one epilogue warp
+  if (op.out_kind == OUT_HALF && !op.add1 && !op.add2 && !op.out2_relu && op.shuffle_n == 0 && op.so == 1 && op.oy == 0 &&
+      op.ox == 0 && bn >= 128 && tma_store_enabled() && (op.ldo * 2) % 16 == 0 && ((uintptr_t)op.out & 15) == 0) {
+    const uint64_t n_out = (uint64_t)(op.act == ACT_SWIGLU ? op.N / 2 : op.N);
+    uint64_t dims[4] = {n_out, (uint64_t)op.OW, (uint64_t)op.OH, (uint64_t)op.B};
+    uint64_t str[3] = {(uint64_t)op.ldo * 2, (uint64_t)op.ldo * 2 * op.OW, (uint64_t)op.ldo * 2 * op.OW * op.OH};
+    uint32_t box[4] = {64, (uint32_t)std::min(TW, 32), (uint32_t)std::max(1, 32 / TW), 1};
+    if (!make_tmap(&p.tmOut, op.out, 4, dims, str, box, c.is_bf16, c.err)) return c.fail(c.err);
+    p.tma_store = 1;
+  }
+  p.inv_n_tiles = 1.0f / (float)p.n_tiles;
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x;
+  p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   p.num_taps = op.taps;
   p.kchunks = op.kpad / 64;
   p.a_xoff = op.xoff;
@@ -2177,5 +2200,12 @@ int dpt_allgather_depth(void* nccl_comm, const void* local_depth, void* global_d
 // trace build only (tools/attn_trace.py): copies the per-phase clock stamps of attn_tc_kernel to the host
 extern "C" int dpt_debug_attn_trace(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, dpt::g_att_trace, sizeof(long long) * 4 * 16 * 10);
+}
+#endif
+
+#ifdef GEMM_TRACE
+// trace build only (tools/gemm_trace.py): copies the clock stamps of gemm_tc_kernel's epilogue warps / MMA thread
+extern "C" int dpt_debug_gemm_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, dpt::g_gemm_trace, sizeof(long long) * 9 * 8 * 16);
 }
 #endif

@@ -84,10 +84,30 @@ struct __align__(64) GemmParams {
   // k <- normalize(k) (F.normalize, eps 1e-12) are applied to the fp32 accumulator before its single 16-bit rounding.
   const float* qk_logit;   // [heads] (already exp'd and clamped), or null
   int qk_features;         // F: columns [0, F) are q, [F, 2F) k, [2F, 3F) v
+  // Plain 16-bit outputs (no addends, no pixel shuffle, BLOCK_N >= 128): each epilogue warp hands its staged 32-row x
+  // 64-column chunk to the TMA (box = the warp's rows inside the tile, 128B swizzle = the staging layout) instead of
+  // 8 shuffle + LDS + STG passes; rows / columns outside the tensor are clipped by the TMA unit.
+  CUtensorMap tmOut;
+  int tma_store;
+  // 1 / n_tiles, 1 / tiles_x, 1 / tiles_y: the tile -> (n, x, y, image) decomposition runs once per tile on the critical
+  // path of the producer and of every epilogue thread; fast_div replaces six integer divisions (~1000 clocks) there
+  float inv_n_tiles, inv_tiles_x, inv_tiles_y;
   float head_w[32];   // OUT_HEAD: depth = act2(relu(acc + bias) . head_w + head_b)
   float head_b;
   int head_act;       // ACT_RELU or ACT_SIGMOID
 };
+
+// -DGEMM_TRACE (tools/gemm_trace.py, never in the shipped library): lane 0 of every epilogue warp and the MMA thread of
+// one CTA stamp clock64() at the phase boundaries of their first eight tiles.
+#ifdef GEMM_TRACE
+__device__ long long g_gemm_trace[9][8][16];  // [epilogue warp 0..7 | 8 = MMA issuer][tile][stamp]
+#define GEMM_STAMP(role, it_, k_)                                            \
+  do {                                                                       \
+    if (trace_cta && (it_) < 8) g_gemm_trace[role][it_][k_] = clock64();     \
+  } while (0)
+#else
+#define GEMM_STAMP(role, it_, k_) do { } while (0)
+#endif
 
 // TWO_CTA: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of
 // A and HALF of the B tile (the tensor core reads the other half from the peer's shared memory), which cuts the
@@ -156,6 +176,15 @@ DPT_DEVICE float2 gelu_erf2(float2 x) {
   return __ffma2_rn(nh, rr, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
+// floor(n / d) for 0 <= n < 2^23, d >= 1, inv = 1.0f / d: the float product is off by at most one either way
+DPT_DEVICE int fast_div(int n, int d, float inv) {
+  int q = (int)((float)n * inv);
+  const int r = n - q * d;
+  if (r < 0) --q;
+  else if (r >= d) ++q;
+  return q;
+}
+
 DPT_DEVICE uint32_t pack2(float a, float b, int is_bf16) {
   if (is_bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -198,6 +227,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef GEMM_TRACE
+  const bool trace_cta = blockIdx.x == 4 && lane == 0;
+#endif
 
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
   const int num_kb = p.num_taps * p.kchunks;
@@ -215,6 +247,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
+    if (p.tma_store) prefetch_tmap(&p.tmOut);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -249,12 +282,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       uint32_t ph = 0;
       const int TW = 1 << p.tw_log2, TH = GEMM_BLOCK_M >> p.tw_log2;
       for (int tile = work_first; tile < total_tiles; tile += work_stride) {
-        const int n_blk = tile % p.n_tiles;
-        int mt = (tile / p.n_tiles) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
-        const int tx = mt % p.tiles_x;
-        mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int b = mt / p.tiles_y;  // == p.B for the odd trailing M-tile of a pair: TMA zero-fills
+        const int m_idx = fast_div(tile, p.n_tiles, p.inv_n_tiles);
+        const int n_blk = tile - m_idx * p.n_tiles;
+        const int mt = m_idx * (TWO_CTA ? 2 : 1) + (int)cta_rank;
+        const int mrow = fast_div(mt, p.tiles_x, p.inv_tiles_x);
+        const int tx = mt - mrow * p.tiles_x;
+        const int b = fast_div(mrow, p.tiles_y, p.inv_tiles_y);  // == p.B for the odd trailing M-tile of a pair: TMA zero-fills
+        const int ty = mrow - b * p.tiles_y;
         const int x0 = tx * TW + p.a_xoff, y0 = ty * TH;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int dy = p.num_taps == 9 ? tap / 3 - 1 : 0;
@@ -301,10 +335,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const uint32_t aph = ACC_STAGES == 2 ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
+        GEMM_STAMP(8, it, 0);
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (kb == 0) GEMM_STAMP(8, it, 1);
           const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES));
           const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES));
           const uint64_t b_desc_hi = WIDE ? make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES + 16384)) : 0;
@@ -323,6 +359,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         if constexpr (TWO_CTA) umma_commit_2sm(&tmem_full[as]);
         else umma_commit(&tmem_full[as]);
+        GEMM_STAMP(8, it, 2);
       }
     }
     __syncwarp();
@@ -345,26 +382,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     constexpr int NV = (BLOCK_N + GEMM_EPI_WARPS * 32 - 1) / (GEMM_EPI_WARPS * 32);
     struct EpiTile {
       int n_blk, b, n_base;
+      int wx, wy;  // output (x, y) of this warp's first row (TMA store box origin)
       long long pix;
       bool row_ok;
       float bias_v[NV], cs_v[NV];
       float4 st4[4];
     };
     auto fetch_tile = [&](int tile, EpiTile& t) {
-      t.n_blk = tile % p.n_tiles;
-      int mt = (tile / p.n_tiles) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      t.b = mt / p.tiles_y;
+      const int m_idx = fast_div(tile, p.n_tiles, p.inv_n_tiles);
+      t.n_blk = tile - m_idx * p.n_tiles;
+      const int mt = m_idx * (TWO_CTA ? 2 : 1) + (int)cta_rank;
+      const int mrow = fast_div(mt, p.tiles_x, p.inv_tiles_x);
+      const int tx = mt - mrow * p.tiles_x;
+      t.b = fast_div(mrow, p.tiles_y, p.inv_tiles_y);
+      const int ty = mrow - t.b * p.tiles_y;
       // output pixel of my row
       const int x = tx * TW + (r & (TW - 1));
       const int y = ty * TH + (r >> p.tw_log2);
       t.row_ok = (x < p.W) && (y < p.H) && (t.b < p.B);
+      t.wx = tx * TW + ((q * 32) & (TW - 1));
+      t.wy = ty * TH + ((q * 32) >> p.tw_log2);
       // pixel-shuffle target: fixed per launch, or chosen by the n-tile (merged ConvTranspose)
-      const int sub_px = p.shuffle_n > 0 ? (t.n_blk * BLOCK_N) / p.shuffle_n : 0;
-      const int sh_oy = p.shuffle_n > 0 ? sub_px / p.so : p.oy, sh_ox = p.shuffle_n > 0 ? sub_px % p.so : p.ox;
-      t.n_base = p.shuffle_n > 0 ? t.n_blk * BLOCK_N - sub_px * p.shuffle_n : t.n_blk * BLOCK_N;  // channel of column 0
+      int sh_oy = p.oy, sh_ox = p.ox;
+      t.n_base = t.n_blk * BLOCK_N;  // channel of column 0
+      if (p.shuffle_n > 0) {
+        const int sub_px = (t.n_blk * BLOCK_N) / p.shuffle_n;
+        sh_oy = sub_px / p.so;
+        sh_ox = sub_px % p.so;
+        t.n_base -= sub_px * p.shuffle_n;
+      }
       t.pix = ((long long)t.b * p.OH + (long long)y * p.so + sh_oy) * p.OW + (long long)x * p.so + sh_ox;
       // folded LayerNorm: the partial statistics of my row (ln_parts is even: two (sum, sum sq) pairs per 16-byte load)
       const bool has_ln = p.ln_stats != nullptr && t.row_ok;
@@ -388,10 +434,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     for (int tile = work_first; tile < total_tiles; tile += work_stride, ++it) {
       const int as = ACC_STAGES == 2 ? (it & 1) : 0;
       const uint32_t aph = ACC_STAGES == 2 ? ((it >> 1) & 1) : (it & 1);
+      GEMM_STAMP(ew, it, 0);
       const int n_blk = cur.n_blk, b = cur.b, n_base = cur.n_base;
       const long long pix = cur.pix;
       const bool row_ok = cur.row_ok;
-      (void)b;
+      const int wx = cur.wx, wy = cur.wy;
+      (void)b; (void)wx; (void)wy;
 
       // bias / column-sum vectors -> smem. Single-buffered: the first barrier waits until every epilogue warp is done
       // with the previous tile's vectors.
@@ -427,8 +475,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_f - mean * mean, 0.0f) + p.ln_eps);
         ln_rm = -ln_rstd * mean;
       }
-      // the next tile's operands: in flight while this tile's units are processed
-      if (tile + work_stride < total_tiles) fetch_tile(tile + work_stride, cur);
+      GEMM_STAMP(ew, it, 1);
+      // The next tile's operands are fetched while this tile's units are processed: right after the first unit's math
+      // (below), where the ~100 instructions of address arithmetic interleave with it instead of sitting, latency-bound,
+      // between the barriers and the accumulator wait. Warps without units of their own fetch here.
+      const bool fetch_in_units = wg_active && OUT_KIND != OUT_HEAD;
+      if (!fetch_in_units && tile + work_stride < total_tiles) fetch_tile(tile + work_stride, cur);
 
       // OUT_F32: rows 4*i + (lane >> 3) of this warp are the ones this lane moves in the coalesced phase. The fp32
       // residual of a 32-column unit is fetched one unit ahead with cp.async into a per-warp buffer (unit 0: before the
@@ -462,6 +514,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
+      GEMM_STAMP(ew, it, 2);
 
       if (wg_active) {
         const int col_base = wg * COLS_PER_WG;  // within the tile
@@ -510,6 +563,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               if (u > 0) tmem_ld32(t_acc + u * 32, vbuf[0]);
             }
             tmem_ld_wait_dep(v);
+            if (u < 4) GEMM_STAMP(ew, it, 3 + 3 * u);
             if constexpr (!F32OUT) {
               if (u + 1 < UNITS) tmem_ld32(t_acc + (u + 1) * 32, vbuf[(u + 1) & 1]);
             }
@@ -596,6 +650,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                       make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
                 }
               } else {
+                if (p.tma_store && (u % UNITS_PER_STG) == (SWI ? 1 : 0)) {
+                  // first write into the staging chunk: the TMA store of the previous chunk must have read it
+                  if (lane == 0) bulk_wait_read_all();
+                  __syncwarp();
+                }
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                   const int phys = ((cc >> 3) + ch) ^ (lane & 7);
@@ -608,6 +667,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 }
               }
             }
+            if (u == (SWI ? 1 : 0) && tile + work_stride < total_tiles) fetch_tile(tile + work_stride, cur);  // see above
+            if (u < 4) GEMM_STAMP(ew, it, 4 + 3 * u);
             if ((u % UNITS_PER_STG) != UNITS_PER_STG - 1) continue;  // staging chunk not complete yet
             __syncwarp();
             // ---- phase 2: coalesced global IO; 8 lanes cover one 128-byte row segment, 4 rows per pass, all
@@ -677,6 +738,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                   }
                 }
               }
+            } else if (NCOLS_HERE == 64 && p.tma_store) {
+              fence_proxy_async_smem();  // the staging writes (generic proxy) -> visible to the TMA (async proxy)
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&p.tmOut, stg, ncol0, wx, wy, b);
+                bulk_commit();
+              }
             } else {
               const bool has_extra = p.add1 != nullptr || p.add2 != nullptr || p.out2_relu != nullptr;
 #pragma unroll
@@ -687,8 +755,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const int rr = 16 * hb + 4 * i + (lane >> 3);
+#if defined(GEMM_ABL) && GEMM_ABL == 2  // timing ablation only (wrong rows): no shuffles
+                  rpix[i] = pix + rr;
+                  ok[i] = row_ok && col_ok;
+#else
                   rpix[i] = __shfl_sync(0xffffffffu, pix, rr);
                   ok[i] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
+#endif
                   val[i] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((sub ^ (rr & 7)) * 16));
                 }
                 if (has_extra) {
@@ -725,12 +798,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                       *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2_relu) + rpix[i] * p.ld_out2 + coff) = rv;
                   }
                 }
+#if defined(GEMM_ABL) && GEMM_ABL == 1  // timing ablation only: the stores happen for impossible values
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (ok[i] && val[i].x == 0x7fc07fc1u) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
+#else
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                   if (ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + rpix[i] * p.ldo + coff) = val[i];
+#endif
               }
             }
             __syncwarp();
+            if (u < 4) GEMM_STAMP(ew, it, 5 + 3 * u);
           }
           if constexpr (F32OUT) {
             if (p.stats_out != nullptr) {
@@ -750,6 +830,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      GEMM_STAMP(ew, it, 15);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -759,6 +840,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   }
 
+  if (p.tma_store && warp_idx >= 2 && lane == 0) bulk_wait_all();  // my TMA stores have left shared memory and landed
   tc_fence_before();
   if constexpr (TWO_CTA) cluster_sync_all();  // the peer's smem / TMEM stay valid until both CTAs are done
   else __syncthreads();

@@ -159,6 +159,16 @@ DPT_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// TMA store (shared -> global, bulk async-group completion): out-of-bounds elements of the box are not written
+DPT_DEVICE void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+DPT_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DPT_DEVICE void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // smem reusable
+DPT_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }            // writes done
+
 // ---------------------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, ld, fences
 
