@@ -4,7 +4,7 @@ tile, when the epilogue got its operands, how long it waited for the accumulator
 (TMEM load wait | bias / LayerNorm fold / activation / pack / staging | coalesced global IO), and how long the MMA thread
 waited for a free accumulator stage. The stamps are global stores by one lane per warp - cheap, but not free: read the
 phase lengths relative to each other.
-usage (GPU box): python tools/gemm_trace.py [M K N act]     (re)builds muggled_dpt_b200/lib/libdpt_b200_trace.so when stale"""
+usage (GPU box): python tools/gemm_trace.py [M K N act [f32]]     (re)builds muggled_dpt_b200/lib/libdpt_b200_trace.so when stale"""
 import ctypes
 import os
 import subprocess
@@ -27,11 +27,19 @@ from gpu_util import conv_gemm  # noqa: E402
 from muggled_dpt_b200.weights import pack_linear  # noqa: E402
 
 M, K, N, act = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 else (10376, 768, 3072, 1)
+f32_residual = len(sys.argv) >= 6 and sys.argv[5] == "f32"  # fp32 output with an in-place fp32 residual (proj / fc2)
 A = torch.randn(1, 1, M, K, device="cuda").to(torch.bfloat16)
 W = pack_linear((torch.randn(N, K) * K**-0.5).to(torch.bfloat16)).cuda()
 bias = torch.randn(N, device="cuda")
+x = torch.randn(M, N, device="cuda")
 for _ in range(3):
-    conv_gemm(A, W, bias, act=act)
+    if f32_residual:
+        rc = native.lib().dpt_op_conv_gemm(A.data_ptr(), W.data_ptr(), bias.data_ptr(), x.data_ptr(), x.data_ptr(), None, None,
+                                           1, 1, M, K, N, 1, 0, 0, 1, native.DPT_BF16,
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        native.check(rc, None, "gemm")
+    else:
+        conv_gemm(A, W, bias, act=act)
 torch.cuda.synchronize()
 handle = ctypes.CDLL(lib)
 buf = (ctypes.c_longlong * (9 * 8 * 16))()
@@ -42,7 +50,7 @@ def g(role, it, k):
     return buf[(role * 8 + it) * 16 + k]
 
 
-print(f"GEMM M={M} K={K} N={N} act={act}: CTA 4, clocks")
+print(f"GEMM M={M} K={K} N={N} act={act}{' fp32 out + in-place residual' if f32_residual else ''}: CTA 4, clocks")
 t00 = g(8, 0, 0)
 print("MMA thread: per tile  [wait acc stage -> first operands ready -> all MMAs issued]")
 for it in range(8):
