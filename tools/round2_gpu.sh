@@ -18,7 +18,11 @@ timeout 600 python bench.py --impl reference-gpu --steps 10 --warmup 3 > $OUT/be
 timeout 300 python bench.py --model vitb --batch 8 --steps 20 --no-cpu-baseline --dump-profile $OUT/launch_table_vitb.csv > $OUT/bench_vitb.json 2>> $OUT/bench_configs.err; summ $OUT/bench_vitb.json vitb_b8
 timeout 300 python bench.py --model beit_large_384 --batch 16 --size 384 --steps 20 --no-cpu-baseline --dump-profile $OUT/launch_table_beit_large_384.csv > $OUT/bench_beit_large_384.json 2>> $OUT/bench_configs.err; summ $OUT/bench_beit_large_384.json beit_large
 timeout 300 python bench.py --model swinv2_large_384 --batch 16 --size 384 --dtype fp16 --steps 20 --no-cpu-baseline --dump-profile $OUT/launch_table_swinv2_large_384.csv > $OUT/bench_swinv2_large_384.json 2>> $OUT/bench_configs.err; summ $OUT/bench_swinv2_large_384.json swinv2_large
-timeout 300 python bench.py --batch 4 --steps 20 --no-cpu-baseline > $OUT/bench_vitl_b4.json 2>> $OUT/bench_configs.err; summ $OUT/bench_vitl_b4.json vitl_b4
+timeout 300 python bench.py --batch 4 --steps 20 --no-cpu-baseline --dump-profile $OUT/launch_table_vitl_b4.csv > $OUT/bench_vitl_b4.json 2>> $OUT/bench_configs.err; summ $OUT/bench_vitl_b4.json vitl_b4
+timeout 300 python bench.py --batch 1 --steps 20 --warmup 5 --no-cpu-baseline --dump-profile $OUT/launch_table_vitl_b1.csv > $OUT/bench_vitl_b1.json 2>> $OUT/bench_configs.err; summ $OUT/bench_vitl_b1.json vitl_b1
+timeout 300 python bench.py --model vits --batch 1 --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_vits_b1.json 2>> $OUT/bench_configs.err; summ $OUT/bench_vits_b1.json vits_b1
+timeout 300 python bench.py --model vits --batch 32 --steps 20 --no-cpu-baseline > $OUT/bench_vits_b32.json 2>> $OUT/bench_configs.err; summ $OUT/bench_vits_b32.json vits_b32
+timeout 400 python bench.py --model vitg --batch 16 --steps 5 --warmup 3 --no-cpu-baseline --dump-profile $OUT/launch_table_vitg_b16.csv > $OUT/bench_vitg_b16.json 2>> $OUT/bench_configs.err; summ $OUT/bench_vitg_b16.json vitg_b16
 timeout 300 python tools/bench_prepost.py > $OUT/bench_prepost.json 2>> $OUT/bench_configs.err
 timeout 600 python tools/parity_report.py $OUT/parity_report.json SBLWE > $OUT/parity_report.txt 2>&1; tail -10 $OUT/parity_report.txt
 export DPT_GRAPH=0
