@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "muggled_dpt_b200", "lib", "libdpt_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
-WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTCBAR", "UTCATOMSWS", "MUFU.EX2", "FFMA2", "SYNCS", "HMMA", "HGMMA", "LDGSTS"]
+WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCATOMSWS", "MUFU.EX2", "FFMA2", "SYNCS", "HMMA", "HGMMA", "LDGSTS"]
 kernels = collections.OrderedDict()
 name = None
 for line in sass.splitlines():
@@ -31,9 +31,9 @@ for line in sass.splitlines():
                 kernels[name][w] += 1
 tot = collections.Counter()
 print(f"# SASS opcode counts per kernel of {os.path.relpath(lib, ROOT)} (cuobjdump -sass, sm_100a); {len(kernels)} kernels")
-print("# UTCHMMA = tcgen05.mma kind::f16, LDTM/STTM = tcgen05.ld/st, UTMALDG = cp.async.bulk.tensor (TMA), LDGSTS = cp.async;")
+print("# UTCHMMA = tcgen05.mma kind::f16, LDTM/STTM = tcgen05.ld/st, UTMALDG / UTMASTG = cp.async.bulk.tensor loads / stores (TMA), LDGSTS = cp.async;")
 print("# HMMA (mma.sync) / HGMMA (wgmma) would be legacy tensor paths: none expected")
-cols = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "LDGSTS", "MUFU.EX2", "FFMA2", "HMMA", "HGMMA", "_total"]
+cols = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "LDGSTS", "MUFU.EX2", "FFMA2", "HMMA", "HGMMA", "_total"]
 print("kernel," + ",".join(cols))
 for k, c in kernels.items():
     if c["UTCHMMA"] or c["UTMALDG"] or c["LDTM"]:

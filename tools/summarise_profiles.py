@@ -30,7 +30,11 @@ for a, b in [("bench_vitl_b32.json", f"{rnd}_bench_vitl_b32_504.json"), ("bench_
              ("launch_table_swinv2_large_384.csv", f"{rnd}_launch_table_swinv2_large_384.csv"),
              ("bench_reference_cpu.json", f"{rnd}_bench_reference_cpu_arm.json"),
              ("bench_reference_gpu_eager.json", f"{rnd}_bench_reference_gpu_eager_vitl_b32.json"),
-             ("parity_report.json", f"{rnd}_parity_report_five_configs.json")]:
+             ("parity_report.json", f"{rnd}_parity_report_five_configs.json"),
+             ("bench_vitl_b1.json", f"{rnd}_bench_vitl_b1_504.json"), ("launch_table_vitl_b1.csv", f"{rnd}_launch_table_vitl_b1_504.csv"),
+             ("launch_table_vitl_b4.csv", f"{rnd}_launch_table_vitl_b4_504.csv"),
+             ("bench_vits_b1.json", f"{rnd}_bench_vits_b1_504.json"), ("bench_vits_b32.json", f"{rnd}_bench_vits_b32_504.json"),
+             ("bench_vitg_b16.json", f"{rnd}_bench_vitg_B16.json"), ("launch_table_vitg_b16.csv", f"{rnd}_launch_table_vitg_B16.csv")]:
     copy(a, b)
 
 
