@@ -595,6 +595,7 @@ bool add_gemm(Ctx& c, GemmOp op) {
   p.head_act = op.head_act;
 
   const long long total = (long long)p.B * p.tiles_y * p.tiles_x * p.n_tiles;
+  if (total >= (1ll << 23)) return c.fail("gemm: more than 2^23 tiles (the kernel's fast tile decomposition is exact below that)");
   int grid = (int)std::min<long long>(total, c.num_sms);
   if (two_cta) grid = (int)std::min<long long>(2 * ((m_tiles_all + 1) / 2) * n_tiles_all, c.num_sms & ~1);
 
